@@ -1,0 +1,104 @@
+// Per-proof Groth16 verification (one proof per thread in the v1 kernels).
+// Replaces verify_groth16 / prepare_inputs (reference verifier/src/groth16/verify.rs:53-78) and the
+// per-proof half of load_groth16_proof_from_bytes (verifier/src/groth16/converter.rs:14-26).
+//
+// GPU shape (same mathematical values, VK-constant work hoisted to vk_load):
+//   target  = e(alpha, beta')             computed once per VK  (reference recomputes it per call, :70)
+//   lines   = G2::precompute(gamma'), G2::precompute(delta')    once per VK
+//   verdict = FE( ML[(A,B), (L,gamma'), (C,delta')] ) == target
+// where (beta', gamma', delta') = (-beta_file, gamma, -delta) for the reference equation and
+// (beta_file, -gamma, -delta) for gnark's (sign_mode 1).
+#pragma once
+#include "io.cuh"
+#include "pairing.cuh"
+
+namespace bn254 {
+
+#define BN_MAX_IC 9  // up to 8 public inputs
+
+struct Groth16VkDev {
+  int n_ic;
+  G1Aff alpha;
+  G2Aff beta, gamma, delta;  // already sign-adjusted (beta', gamma', delta')
+  G1Aff ic[BN_MAX_IC];
+  Fp12 target;               // e(alpha, beta')
+  Line gamma_lines[BN_N_LINES];
+  Line delta_lines[BN_N_LINES];
+};
+
+// VK-constant precomputation (runs once per VK, single thread).
+HD void groth16_vk_prepare(Groth16VkDev& vk) {
+  g2_precompute(vk.gamma_lines, vk.gamma);
+  g2_precompute(vk.delta_lines, vk.delta);
+  Fp12 f = miller_loop<1, 0>(&vk.alpha, &vk.beta, nullptr, nullptr);
+  vk.target = final_exponentiation(f);
+}
+
+// L = IC_0 + sum x_i IC_{i+1}; affine accumulation semantics of the reference: an identity term
+// (x_i == 0) or an identity partial sum panics inside substrate-bn.
+HD int groth16_prepare_inputs(G1Aff& L, const Groth16VkDev& vk, const uint8_t* inputs_be, int n_inputs) {
+  if (n_inputs + 1 != vk.n_ic) return BN254V_ERR_PREPARE_INPUTS;
+  G1Jac acc = to_jac(vk.ic[0]);
+  for (int i = 0; i < n_inputs; i++) {
+    Fr x;
+    if (!fr_load_be_plain(x, inputs_be + 32 * i)) return BN254V_PANIC_FIELD_NOT_MEMBER;
+    G1Jac term = scalar_mul(vk.ic[i + 1], x.v);
+    if (is_identity(term)) return BN254V_PANIC_IDENTITY;
+    acc = jac_add(acc, term);
+    if (is_identity(acc)) return BN254V_PANIC_IDENTITY;
+  }
+  to_affine(L, acc);
+  return BN254V_OK_TRUE;
+}
+
+struct Groth16Debug {
+  uint8_t* L;       // 64 B or null
+  uint8_t* miller;  // 384 B or null
+  uint8_t* gt;      // 384 B or null
+};
+
+// proof: >= 256 bytes (A | B | C), proof_len: valid bytes.
+HD int groth16_verify_one(const Groth16VkDev& vk, const uint8_t* proof, uint32_t proof_len,
+                          const uint8_t* inputs_be, int n_inputs, const Groth16Debug& dbg) {
+  if (proof_len < 256) return BN254V_PANIC_SHORT_BUFFER;
+  G1Aff A, C;
+  G2Aff B;
+  int st = load_g1_checked(A, proof);
+  if (st != BN254V_OK_TRUE) return st;
+  st = load_g2_checked(B, proof + 64);
+  if (st != BN254V_OK_TRUE) return st;
+  st = load_g1_checked(C, proof + 192);
+  if (st != BN254V_OK_TRUE) return st;
+
+  G1Aff L;
+  st = groth16_prepare_inputs(L, vk, inputs_be, n_inputs);
+  if (st != BN254V_OK_TRUE) return st;
+  if (dbg.L) store_g1(dbg.L, L);
+
+  G1Aff pf[2] = {L, C};
+  const Line* tabs[2] = {vk.gamma_lines, vk.delta_lines};
+  Fp12 f = miller_loop<1, 2>(&A, &B, pf, tabs);
+  if (dbg.miller) fp12_to_bytes(dbg.miller, f);
+  Fp12 gt = final_exponentiation(f);
+  if (dbg.gt) fp12_to_bytes(dbg.gt, gt);
+  return eq(gt, vk.target) ? BN254V_OK_TRUE : BN254V_OK_FALSE;
+}
+
+// Raw k-pair product (bn::pairing_batch): all G2 variable.  A pair whose G1 bytes are all zero is
+// skipped (identity).  Returns is_one.
+template <int KP>
+HD bool pairing_product_one(const uint8_t* g1, const uint8_t* g2, uint8_t* miller_out, uint8_t* gt_out) {
+  G1Aff p[KP];
+  G2Aff q[KP];
+  for (int j = 0; j < KP; j++) {
+    load_g1_unchecked(p[j], g1 + 64 * j);
+    load_g2_unchecked(q[j], g2 + 128 * j);
+  }
+  Fp12 f = miller_loop<KP, 0>(p, q, nullptr, nullptr);
+  if (miller_out) fp12_to_bytes(miller_out, f);
+  Fp12 gt = final_exponentiation(f);
+  if (gt_out) fp12_to_bytes(gt_out, gt);
+  return eq(gt, fp12_one());
+}
+
+}  // namespace bn254

@@ -1,0 +1,169 @@
+// Optimal-ate multi-Miller loop and final exponentiation -- the GPU replacement for
+// bn::pairing / bn::pairing_batch (reference call sites verifier/src/groth16/verify.rs:70,73 and
+// verifier/src/plonk/kzg.rs:180-187).  Formulas follow substrate-bn's flipped Miller loop
+//  so that the canonical Fq12 Miller value is bit-identical:
+//   * homogeneous projective doubling / mixed-addition steps with line (ell_0, ell_vw, ell_vv),
+//   * 64-digit ATE_LOOP_COUNT_NAF followed by the two Frobenius additions,
+//   * one shared Fq12 accumulator for all pairs of a check,
+//   * final exponentiation = easy part + Fuentes-Castaneda hard part with cyclotomic squarings.
+#pragma once
+#include "curve.cuh"
+
+namespace bn254 {
+
+struct Line {
+  Fp2 ell_0, ell_vw, ell_vv;
+};
+
+// R <- 2R, returns the tangent line coefficients.
+HD Line doubling_step(G2Jac& r) {
+  Fp2 a = fp2_halve(mul(r.x, r.y));
+  Fp2 b = sqr(r.y);
+  Fp2 c = sqr(r.z);
+  Fp2 d = add(dbl(c), c);
+  Fp2 e = mul(fp2_b2(), d);
+  Fp2 f = add(dbl(e), e);
+  Fp2 g = fp2_halve(add(b, f));
+  Fp2 h = sub(sqr(add(r.y, r.z)), add(b, c));
+  Fp2 i = sub(e, b);
+  Fp2 j = sqr(r.x);
+  Fp2 e2 = sqr(e);
+  r.x = mul(a, sub(b, f));
+  r.y = sub(sqr(g), add(dbl(e2), e2));
+  r.z = mul(b, h);
+  return Line{mul_xi(i), neg(h), add(dbl(j), j)};
+}
+
+// R <- R + Q (Q affine), returns the chord line coefficients.
+HD Line addition_step(G2Jac& r, const G2Aff& q) {
+  Fp2 d = sub(r.x, mul(r.z, q.x));
+  Fp2 e = sub(r.y, mul(r.z, q.y));
+  Fp2 f = sqr(d);
+  Fp2 g = sqr(e);
+  Fp2 h = mul(d, f);
+  Fp2 i = mul(r.x, f);
+  Fp2 j = sub(add(mul(r.z, g), h), dbl(i));
+  Fp2 ell0 = mul_xi(sub(mul(e, q.x), mul(d, q.y)));
+  r.x = mul(d, j);
+  r.y = sub(mul(e, sub(i, j)), mul(h, r.y));
+  r.z = mul(r.z, h);
+  return Line{ell0, d, neg(e)};
+}
+
+HD G2Aff g2_mul_by_q(const G2Aff& q) { return g2_psi(q); }
+
+// f <- f * line(P): mul_by_024(ell_0, ell_vw * P.y, ell_vv * P.x)
+HD void apply_line(Fp12& f, const Line& l, const G1Aff& p) {
+  f = mul_by_024(f, l.ell_0, scale(l.ell_vw, p.y), scale(l.ell_vv, p.x));
+}
+
+#define BN_N_LINES 87
+
+// G2::precompute -> 87 line triples for a fixed (VK-constant) G2 point.
+HD void g2_precompute(Line* out, const G2Aff& q) {
+  G2Jac r = to_jac(q);
+  G2Aff nq = neg(q);
+  int idx = 0;
+  for (int k = 0; k < 64; k++) {
+    out[idx++] = doubling_step(r);
+    int d = K::ate_digit(k);
+    if (d == 1) out[idx++] = addition_step(r, q);
+    else if (d == 3) out[idx++] = addition_step(r, nq);
+  }
+  G2Aff q1 = g2_mul_by_q(q);
+  G2Aff q2 = neg(g2_mul_by_q(q1));
+  out[idx++] = addition_step(r, q1);
+  out[idx++] = addition_step(r, q2);
+}
+
+// Shared-accumulator Miller loop over NV pairs with a variable G2 point (lines computed on the
+// fly) and NF pairs whose G2 point has a precomputed line table.
+// `active_v` / `active_f`: pairs with an identity member are skipped (substrate-bn pairing_batch).
+template <int NV, int NF>
+HD Fp12 miller_loop(const G1Aff* pv, const G2Aff* qv, const G1Aff* pf, const Line* const* tables) {
+  Fp12 f = fp12_one();
+  G2Jac r[NV > 0 ? NV : 1];
+  G2Aff nq[NV > 0 ? NV : 1];
+  for (int v = 0; v < NV; v++) {
+    r[v] = to_jac(qv[v]);
+    nq[v] = neg(qv[v]);
+  }
+  int idx = 0;
+  for (int k = 0; k < 64; k++) {
+    f = sqr(f);
+    for (int v = 0; v < NV; v++) {
+      Line l = doubling_step(r[v]);
+      apply_line(f, l, pv[v]);
+    }
+    for (int t = 0; t < NF; t++) apply_line(f, tables[t][idx], pf[t]);
+    idx++;
+    int d = K::ate_digit(k);
+    if (d != 0) {
+      for (int v = 0; v < NV; v++) {
+        Line l = addition_step(r[v], d == 1 ? qv[v] : nq[v]);
+        apply_line(f, l, pv[v]);
+      }
+      for (int t = 0; t < NF; t++) apply_line(f, tables[t][idx], pf[t]);
+      idx++;
+    }
+  }
+  // Frobenius additions: all pairs consume coefficient idx (Q1) then idx+1 (Q2), as
+  // substrate-bn's miller_loop_batch shares the coefficient index across pairs.
+  G2Aff q1[NV > 0 ? NV : 1], q2[NV > 0 ? NV : 1];
+  for (int v = 0; v < NV; v++) {
+    q1[v] = g2_mul_by_q(qv[v]);
+    q2[v] = neg(g2_mul_by_q(q1[v]));
+  }
+  for (int v = 0; v < NV; v++) {
+    Line l = addition_step(r[v], q1[v]);
+    apply_line(f, l, pv[v]);
+  }
+  for (int t = 0; t < NF; t++) apply_line(f, tables[t][idx], pf[t]);
+  idx++;
+  for (int v = 0; v < NV; v++) {
+    Line l = addition_step(r[v], q2[v]);
+    apply_line(f, l, pv[v]);
+  }
+  for (int t = 0; t < NF; t++) apply_line(f, tables[t][idx], pf[t]);
+  return f;
+}
+
+// conj(a^x), x = BN parameter, square-and-multiply with cyclotomic squarings
+HD Fp12 exp_by_neg_z(const Fp12& a) {
+  Fp12 r = a;  // leading one of x (bit 62)
+  for (int i = 61; i >= 0; i--) {
+    r = cyclotomic_sqr(r);
+    if ((K::bn_x >> i) & 1) r = mul(r, a);
+  }
+  return conj(r);
+}
+
+// Fq12::final_exponentiation.  `f` must be non-zero (a Miller value always is).
+HD Fp12 final_exponentiation(const Fp12& f) {
+  Fp12 t = mul(conj(f), inv(f));
+  t = mul(frobenius<2>(t), t);
+  Fp12 a = exp_by_neg_z(t);
+  Fp12 b = cyclotomic_sqr(a);
+  Fp12 c = cyclotomic_sqr(b);
+  Fp12 d = mul(c, b);
+  Fp12 e = exp_by_neg_z(d);
+  Fp12 ff = cyclotomic_sqr(e);
+  Fp12 g = exp_by_neg_z(ff);
+  Fp12 h = conj(d);
+  Fp12 i = conj(g);
+  Fp12 j = mul(i, e);
+  Fp12 k = mul(j, h);
+  Fp12 l = mul(k, b);
+  Fp12 m = mul(k, e);
+  Fp12 n = mul(t, m);
+  Fp12 o = frobenius<1>(l);
+  Fp12 p = mul(o, n);
+  Fp12 q = frobenius<2>(k);
+  Fp12 rr = mul(q, p);
+  Fp12 s = conj(t);
+  Fp12 t2 = mul(s, l);
+  Fp12 u = frobenius<3>(t2);
+  return mul(u, rr);
+}
+
+}  // namespace bn254
