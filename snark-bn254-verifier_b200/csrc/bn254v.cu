@@ -1,0 +1,658 @@
+// bn254v: kernels + C ABI (include/bn254v.h).  sm_100a only; there is no CPU fallback -- every
+// compute entry point fails with BN254V_E_NO_DEVICE when no CUDA device is usable.
+//
+// Kernel shape (v1): one proof per thread.  Per-proof data is ~0.3 KB in / 1 B out, so HBM traffic is
+// negligible; the bound is the SM's 32-bit integer multiply-add pipe.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "gnark_host.h"
+#include "groth16.cuh"
+#include "synth.cuh"
+
+using namespace bn254;
+
+// ------------------------------------------------------------------------------------------------
+// library state
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Dev {
+  int id;
+  cudaStream_t stream;
+  cudaEvent_t ev0, ev1;
+};
+
+std::mutex g_mu;
+std::vector<Dev> g_devs;
+bool g_inited = false;
+std::atomic<uint64_t> g_launches{0};
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t _e = (call);                                                                  \
+    if (_e != cudaSuccess) return fail(BN254V_E_CUDA, "%s: %s", #call, cudaGetErrorString(_e)); \
+  } while (0)
+
+int ensure_init() {
+  if (g_inited) return 0;
+  return bn254v_init(nullptr, 0);
+}
+
+struct DevBuf {  // RAII device allocation on the current device
+  void* p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+  template <class T>
+  T* as() { return (T*)p; }
+};
+
+// contiguous shard [lo, hi) of n items for device slot d of nd
+inline void shard(size_t n, int d, int nd, size_t& lo, size_t& hi) {
+  lo = n * (size_t)d / nd;
+  hi = n * (size_t)(d + 1) / nd;
+}
+
+}  // namespace
+
+struct bn254v_vk {
+  int kind;  // 0 groth16, 1 plonk
+  int n_public;
+  int sign_mode;
+  std::vector<void*> dev;  // per device slot: Groth16VkDev* / PlonkVkDev*
+};
+
+struct bn254v_batch {
+  size_t n;
+  int n_inputs;
+  struct Part {
+    size_t lo, hi;
+    uint8_t *proofs, *inputs, *status;
+  };
+  std::vector<Part> parts;
+};
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+#define BN_TPB 128
+
+__global__ void k_groth16_vk_prepare(Groth16VkDev* vk) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) groth16_vk_prepare(*vk);
+}
+
+__global__ void __launch_bounds__(BN_TPB)
+    k_groth16_verify(const Groth16VkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride,
+                     const uint32_t* __restrict__ proof_len, const uint8_t* __restrict__ inputs, int n_inputs,
+                     size_t n, uint8_t* __restrict__ status, uint8_t* dbg_l, uint8_t* dbg_m, uint8_t* dbg_gt) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Groth16Debug dbg{dbg_l ? dbg_l + 64 * i : nullptr, dbg_m ? dbg_m + 384 * i : nullptr,
+                   dbg_gt ? dbg_gt + 384 * i : nullptr};
+  uint32_t len = proof_len ? proof_len[i] : (uint32_t)stride;
+  if (len > stride) len = (uint32_t)stride;
+  status[i] = (uint8_t)groth16_verify_one(*vk, proofs + stride * i, len, inputs + (size_t)32 * n_inputs * i,
+                                          n_inputs, dbg);
+}
+
+template <int KP>
+__global__ void __launch_bounds__(BN_TPB)
+    k_pairing_product(const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2, size_t n,
+                      uint8_t* __restrict__ is_one, uint8_t* miller_out, uint8_t* gt_out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  is_one[i] = pairing_product_one<KP>(g1 + (size_t)64 * KP * i, g2 + (size_t)128 * KP * i,
+                                      miller_out ? miller_out + 384 * i : nullptr,
+                                      gt_out ? gt_out + 384 * i : nullptr)
+                  ? 1
+                  : 0;
+}
+
+__global__ void __launch_bounds__(BN_TPB)
+    k_groth16_synth(Groth16Trapdoor td, uint64_t seed, size_t first, size_t n, int n_public, int sign_mode,
+                    uint8_t* proofs, uint8_t* inputs, uint8_t* expected) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  groth16_synth_one(proofs + 256 * i, inputs + (size_t)32 * n_public * i, expected + i, td, seed, first + i,
+                    n_public, sign_mode);
+}
+
+__global__ void __launch_bounds__(BN_TPB)
+    k_pairing_synth(uint64_t seed, size_t first, size_t n, int k, uint8_t* g1, uint8_t* g2, uint8_t* expected) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  pairing_synth_one(g1 + (size_t)64 * k * i, g2 + (size_t)128 * k * i, expected + i, seed, first + i, k);
+}
+
+// Dependent-free multiply-add streams: 8 independent accumulators per thread.
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_imad_peak(int iters, uint32_t a0, uint32_t b0, uint64_t* sink) {
+  uint32_t a = a0 + threadIdx.x, b = b0 + blockIdx.x;
+  if (WIDE) {
+    uint64_t acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = j;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a), "r"(b));
+      }
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s ^= acc[j];
+    if (s == 0x123456789abcdefull) sink[0] = s;
+  } else {
+    uint32_t acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = j;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[j]) : "r"(a), "r"(b));
+      }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s ^= acc[j];
+    if (s == 0x12345678u) sink[0] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int bn254v_init(const int* devices, int n_devices) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_inited) return BN254V_SUCCESS;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(BN254V_E_NO_DEVICE, "no CUDA device: %s", e == cudaSuccess ? "count == 0" : cudaGetErrorString(e));
+  std::vector<int> ids;
+  if (devices && n_devices > 0) {
+    for (int i = 0; i < n_devices; i++) {
+      if (devices[i] < 0 || devices[i] >= count) return fail(BN254V_E_BAD_ARG, "device %d out of range", devices[i]);
+      ids.push_back(devices[i]);
+    }
+  } else {
+    for (int i = 0; i < count; i++) ids.push_back(i);
+  }
+  for (int id : ids) {
+    Dev d;
+    d.id = id;
+    CU(cudaSetDevice(id));
+    CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&d.ev0));
+    CU(cudaEventCreate(&d.ev1));
+    g_devs.push_back(d);
+  }
+  g_inited = true;
+  return BN254V_SUCCESS;
+}
+
+void bn254v_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto& d : g_devs) {
+    cudaSetDevice(d.id);
+    cudaStreamDestroy(d.stream);
+    cudaEventDestroy(d.ev0);
+    cudaEventDestroy(d.ev1);
+  }
+  g_devs.clear();
+  g_inited = false;
+}
+
+int bn254v_device_count(void) { return (int)g_devs.size(); }
+const char* bn254v_last_error(void) { return g_err.c_str(); }
+uint64_t bn254v_launch_count(void) { return g_launches.load(); }
+
+const char* bn254v_status_name(int s) {
+  switch (s) {
+    case BN254V_OK_TRUE: return "OK_TRUE";
+    case BN254V_OK_FALSE: return "OK_FALSE";
+    case BN254V_ERR_PREPARE_INPUTS: return "ERR_PREPARE_INPUTS";
+    case BN254V_ERR_BSB22_MISMATCH: return "ERR_BSB22_MISMATCH";
+    case BN254V_ERR_INVALID_WITNESS: return "ERR_INVALID_WITNESS";
+    case BN254V_ERR_INVERSE_NOT_FOUND: return "ERR_INVERSE_NOT_FOUND";
+    case BN254V_ERR_OPENING_POLY_MISMATCH: return "ERR_OPENING_POLY_MISMATCH";
+    case BN254V_ERR_INVALID_NUMBER_OF_DIGESTS: return "ERR_INVALID_NUMBER_OF_DIGESTS";
+    case BN254V_ERR_PAIRING_CHECK_FAILED: return "ERR_PAIRING_CHECK_FAILED";
+    case BN254V_PANIC_FIELD_NOT_MEMBER: return "PANIC_FIELD_NOT_MEMBER";
+    case BN254V_PANIC_NOT_ON_CURVE: return "PANIC_NOT_ON_CURVE";
+    case BN254V_PANIC_NOT_IN_SUBGROUP: return "PANIC_NOT_IN_SUBGROUP";
+    case BN254V_PANIC_IDENTITY: return "PANIC_IDENTITY";
+    case BN254V_PANIC_SHORT_BUFFER: return "PANIC_SHORT_BUFFER";
+    case BN254V_PANIC_DIV_BY_ZERO: return "PANIC_DIV_BY_ZERO";
+    case BN254V_STATUS_UNSET: return "UNSET";
+  }
+  return "?";
+}
+
+// ---- verifying keys ----------------------------------------------------------------------------
+int bn254v_groth16_vk_load(const uint8_t* vk_bytes, size_t len, int sign_mode, bn254v_vk** out) {
+  if (!vk_bytes || !out || (sign_mode != 0 && sign_mode != 1)) return fail(BN254V_E_BAD_ARG, "bad argument");
+  int rc = ensure_init();
+  if (rc) return rc;
+  gnark::Groth16VkHost h;
+  if (gnark::parse_groth16_vk(h, vk_bytes, len)) return fail(BN254V_E_VK_PARSE, "malformed Groth16 VK");
+  if (h.k.empty() || h.k.size() > BN_MAX_IC)
+    return fail(BN254V_E_UNSUPPORTED, "|IC| = %zu outside [1, %d]", h.k.size(), BN_MAX_IC);
+  // h.beta2 is -beta_file (as the reference stores it).  sign_mode 0: (beta', gamma', delta') =
+  // (-beta_file, gamma, -delta); sign_mode 1: (beta_file, -gamma, -delta).
+  Groth16VkDev* hv = new Groth16VkDev();
+  memset(hv, 0, sizeof *hv);
+  hv->n_ic = (int)h.k.size();
+  hv->alpha = h.alpha;
+  hv->beta = sign_mode == 0 ? h.beta2 : neg(h.beta2);
+  hv->gamma = sign_mode == 0 ? h.gamma2 : neg(h.gamma2);
+  hv->delta = neg(h.delta2);
+  for (size_t i = 0; i < h.k.size(); i++) hv->ic[i] = h.k[i];
+  bn254v_vk* vk = new bn254v_vk();
+  vk->kind = 0;
+  vk->n_public = hv->n_ic - 1;
+  vk->sign_mode = sign_mode;
+  for (auto& d : g_devs) {
+    cudaError_t e = cudaSetDevice(d.id);
+    Groth16VkDev* dv = nullptr;
+    if (e == cudaSuccess) e = cudaMalloc(&dv, sizeof(Groth16VkDev));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dv, hv, sizeof(Groth16VkDev), cudaMemcpyHostToDevice, d.stream);
+    if (e == cudaSuccess) {
+      k_groth16_vk_prepare<<<1, 32, 0, d.stream>>>(dv);
+      g_launches++;
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+    if (e != cudaSuccess) {
+      delete hv;
+      bn254v_vk_free(vk);
+      return fail(BN254V_E_CUDA, "vk upload/prepare: %s", cudaGetErrorString(e));
+    }
+    vk->dev.push_back(dv);
+  }
+  delete hv;
+  *out = vk;
+  return BN254V_SUCCESS;
+}
+
+int bn254v_plonk_vk_load(const uint8_t* vk_bytes, size_t len, bn254v_vk** out) {
+  (void)vk_bytes;
+  (void)len;
+  (void)out;
+  return fail(BN254V_E_UNSUPPORTED, "PlonK path not built yet");
+}
+
+void bn254v_vk_free(bn254v_vk* vk) {
+  if (!vk) return;
+  for (size_t i = 0; i < vk->dev.size() && i < g_devs.size(); i++) {
+    cudaSetDevice(g_devs[i].id);
+    cudaFree(vk->dev[i]);
+  }
+  delete vk;
+}
+
+int bn254v_vk_n_public(const bn254v_vk* vk) { return vk ? vk->n_public : -1; }
+
+// ---- Groth16 batch -----------------------------------------------------------------------------
+int bn254v_groth16_verify_batch(const bn254v_vk* vk, const uint8_t* proofs, size_t proof_stride,
+                                const uint32_t* proof_len, const uint8_t* inputs_be, int n_inputs, size_t n,
+                                uint8_t* status, const bn254v_debug* dbg) {
+  if (!vk || vk->kind != 0 || !status || (n && (!proofs || (n_inputs > 0 && !inputs_be))) || n_inputs < 0 ||
+      n_inputs > 64)
+    return fail(BN254V_E_BAD_ARG, "bad argument");
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (n == 0) return BN254V_SUCCESS;
+  const int nd = (int)g_devs.size();
+  struct Part {
+    DevBuf proofs, lens, inputs, status, l, m, gt;
+  };
+  std::vector<Part> parts(nd);
+  const size_t in_bytes = (size_t)32 * n_inputs;
+  for (int d = 0; d < nd; d++) {
+    size_t lo, hi;
+    shard(n, d, nd, lo, hi);
+    size_t m = hi - lo;
+    if (!m) continue;
+    Part& p = parts[d];
+    Dev& dev = g_devs[d];
+    CU(cudaSetDevice(dev.id));
+    CU(p.proofs.alloc(m * proof_stride));
+    CU(p.inputs.alloc(m * in_bytes));
+    CU(p.status.alloc(m));
+    CU(cudaMemcpyAsync(p.proofs.p, proofs + lo * proof_stride, m * proof_stride, cudaMemcpyHostToDevice, dev.stream));
+    if (in_bytes)
+      CU(cudaMemcpyAsync(p.inputs.p, inputs_be + lo * in_bytes, m * in_bytes, cudaMemcpyHostToDevice, dev.stream));
+    if (proof_len) {
+      CU(p.lens.alloc(m * 4));
+      CU(cudaMemcpyAsync(p.lens.p, proof_len + lo, m * 4, cudaMemcpyHostToDevice, dev.stream));
+    }
+    if (dbg && dbg->g1_out) CU(p.l.alloc(m * 64));
+    if (dbg && dbg->miller_out) CU(p.m.alloc(m * 384));
+    if (dbg && dbg->gt_out) CU(p.gt.alloc(m * 384));
+    unsigned grid = (unsigned)((m + BN_TPB - 1) / BN_TPB);
+    k_groth16_verify<<<grid, BN_TPB, 0, dev.stream>>>((const Groth16VkDev*)vk->dev[d], p.proofs.as<uint8_t>(),
+                                                      proof_stride, proof_len ? p.lens.as<uint32_t>() : nullptr,
+                                                      p.inputs.as<uint8_t>(), n_inputs, m, p.status.as<uint8_t>(),
+                                                      p.l.as<uint8_t>(), p.m.as<uint8_t>(), p.gt.as<uint8_t>());
+    g_launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(status + lo, p.status.p, m, cudaMemcpyDeviceToHost, dev.stream));
+    if (p.l.p) CU(cudaMemcpyAsync(dbg->g1_out + lo * 64, p.l.p, m * 64, cudaMemcpyDeviceToHost, dev.stream));
+    if (p.m.p) CU(cudaMemcpyAsync(dbg->miller_out + lo * 384, p.m.p, m * 384, cudaMemcpyDeviceToHost, dev.stream));
+    if (p.gt.p) CU(cudaMemcpyAsync(dbg->gt_out + lo * 384, p.gt.p, m * 384, cudaMemcpyDeviceToHost, dev.stream));
+  }
+  for (int d = 0; d < nd; d++) {
+    CU(cudaSetDevice(g_devs[d].id));
+    CU(cudaStreamSynchronize(g_devs[d].stream));
+  }
+  return BN254V_SUCCESS;
+}
+
+int bn254v_plonk_verify_batch(const bn254v_vk* vk, const uint8_t* proofs, size_t proof_stride,
+                              const uint32_t* proof_len, const uint8_t* inputs_be, int n_inputs,
+                              const uint8_t* rnd_be, size_t n, uint8_t* status, const bn254v_debug* dbg) {
+  (void)vk; (void)proofs; (void)proof_stride; (void)proof_len; (void)inputs_be; (void)n_inputs;
+  (void)rnd_be; (void)n; (void)status; (void)dbg;
+  return fail(BN254V_E_UNSUPPORTED, "PlonK path not built yet");
+}
+
+// ---- raw pairing products ----------------------------------------------------------------------
+int bn254v_pairing_product_batch(const uint8_t* g1, const uint8_t* g2, int k, size_t n, uint8_t* is_one,
+                                 uint8_t* miller_out, uint8_t* gt_out) {
+  if (k < 1 || k > 4 || !is_one || (n && (!g1 || !g2))) return fail(BN254V_E_BAD_ARG, "bad argument");
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (n == 0) return BN254V_SUCCESS;
+  const int nd = (int)g_devs.size();
+  struct Part {
+    DevBuf g1, g2, one, m, gt;
+  };
+  std::vector<Part> parts(nd);
+  for (int d = 0; d < nd; d++) {
+    size_t lo, hi;
+    shard(n, d, nd, lo, hi);
+    size_t m = hi - lo;
+    if (!m) continue;
+    Part& p = parts[d];
+    Dev& dev = g_devs[d];
+    CU(cudaSetDevice(dev.id));
+    CU(p.g1.alloc(m * 64 * k));
+    CU(p.g2.alloc(m * 128 * k));
+    CU(p.one.alloc(m));
+    if (miller_out) CU(p.m.alloc(m * 384));
+    if (gt_out) CU(p.gt.alloc(m * 384));
+    CU(cudaMemcpyAsync(p.g1.p, g1 + lo * 64 * k, m * 64 * k, cudaMemcpyHostToDevice, dev.stream));
+    CU(cudaMemcpyAsync(p.g2.p, g2 + lo * 128 * k, m * 128 * k, cudaMemcpyHostToDevice, dev.stream));
+    unsigned grid = (unsigned)((m + BN_TPB - 1) / BN_TPB);
+#define LAUNCH_PP(KP)                                                                                   \
+  k_pairing_product<KP><<<grid, BN_TPB, 0, dev.stream>>>(p.g1.as<uint8_t>(), p.g2.as<uint8_t>(), m,    \
+                                                         p.one.as<uint8_t>(), p.m.as<uint8_t>(), p.gt.as<uint8_t>())
+    switch (k) {
+      case 1: LAUNCH_PP(1); break;
+      case 2: LAUNCH_PP(2); break;
+      case 3: LAUNCH_PP(3); break;
+      default: LAUNCH_PP(4); break;
+    }
+#undef LAUNCH_PP
+    g_launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(is_one + lo, p.one.p, m, cudaMemcpyDeviceToHost, dev.stream));
+    if (miller_out) CU(cudaMemcpyAsync(miller_out + lo * 384, p.m.p, m * 384, cudaMemcpyDeviceToHost, dev.stream));
+    if (gt_out) CU(cudaMemcpyAsync(gt_out + lo * 384, p.gt.p, m * 384, cudaMemcpyDeviceToHost, dev.stream));
+  }
+  for (int d = 0; d < nd; d++) {
+    CU(cudaSetDevice(g_devs[d].id));
+    CU(cudaStreamSynchronize(g_devs[d].stream));
+  }
+  return BN254V_SUCCESS;
+}
+
+// ---- device-resident batches -------------------------------------------------------------------
+int bn254v_groth16_batch_upload(const bn254v_vk* vk, const uint8_t* proofs, size_t proof_stride,
+                                const uint8_t* inputs_be, int n_inputs, size_t n, bn254v_batch** out) {
+  if (!vk || vk->kind != 0 || !proofs || !out || proof_stride < 256 || n_inputs < 0 || (n_inputs && !inputs_be))
+    return fail(BN254V_E_BAD_ARG, "bad argument");
+  int rc = ensure_init();
+  if (rc) return rc;
+  const int nd = (int)g_devs.size();
+  bn254v_batch* b = new bn254v_batch();
+  b->n = n;
+  b->n_inputs = n_inputs;
+  b->parts.resize(nd);
+  const size_t in_bytes = (size_t)32 * n_inputs;
+  for (int d = 0; d < nd; d++) {
+    auto& p = b->parts[d];
+    shard(n, d, nd, p.lo, p.hi);
+    size_t m = p.hi - p.lo;
+    p.proofs = p.inputs = p.status = nullptr;
+    if (!m) continue;
+    Dev& dev = g_devs[d];
+    cudaError_t e = cudaSetDevice(dev.id);
+    if (e == cudaSuccess) e = cudaMalloc(&p.proofs, m * 256);
+    if (e == cudaSuccess) e = cudaMalloc(&p.inputs, m * in_bytes + 1);
+    if (e == cudaSuccess) e = cudaMalloc(&p.status, m);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DAsync(p.proofs, 256, proofs + p.lo * proof_stride, proof_stride, 256, m, cudaMemcpyHostToDevice,
+                            dev.stream);
+    if (e == cudaSuccess && in_bytes)
+      e = cudaMemcpyAsync(p.inputs, inputs_be + p.lo * in_bytes, m * in_bytes, cudaMemcpyHostToDevice, dev.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(dev.stream);
+    if (e != cudaSuccess) {
+      bn254v_batch_free(b);
+      return fail(BN254V_E_CUDA, "batch upload: %s", cudaGetErrorString(e));
+    }
+  }
+  *out = b;
+  return BN254V_SUCCESS;
+}
+
+int bn254v_groth16_batch_verify(const bn254v_vk* vk, bn254v_batch* b, uint8_t* status, float* kernel_ms) {
+  if (!vk || vk->kind != 0 || !b) return fail(BN254V_E_BAD_ARG, "bad argument");
+  const int nd = (int)g_devs.size();
+  if ((int)b->parts.size() != nd) return fail(BN254V_E_BAD_ARG, "batch was staged for another device set");
+  for (int d = 0; d < nd; d++) {
+    auto& p = b->parts[d];
+    size_t m = p.hi - p.lo;
+    Dev& dev = g_devs[d];
+    CU(cudaSetDevice(dev.id));
+    CU(cudaEventRecord(dev.ev0, dev.stream));
+    if (m) {
+      unsigned grid = (unsigned)((m + BN_TPB - 1) / BN_TPB);
+      k_groth16_verify<<<grid, BN_TPB, 0, dev.stream>>>((const Groth16VkDev*)vk->dev[d], p.proofs, 256, nullptr,
+                                                        p.inputs, b->n_inputs, m, p.status, nullptr, nullptr, nullptr);
+      g_launches++;
+      CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(dev.ev1, dev.stream));
+  }
+  float worst = 0.f;
+  for (int d = 0; d < nd; d++) {
+    Dev& dev = g_devs[d];
+    CU(cudaSetDevice(dev.id));
+    CU(cudaStreamSynchronize(dev.stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, dev.ev0, dev.ev1));
+    if (ms > worst) worst = ms;
+  }
+  if (kernel_ms) *kernel_ms = worst;
+  if (status) {
+    for (int d = 0; d < nd; d++) {
+      auto& p = b->parts[d];
+      if (p.hi == p.lo) continue;
+      CU(cudaSetDevice(g_devs[d].id));
+      CU(cudaMemcpy(status + p.lo, p.status, p.hi - p.lo, cudaMemcpyDeviceToHost));
+    }
+  }
+  return BN254V_SUCCESS;
+}
+
+void bn254v_batch_free(bn254v_batch* b) {
+  if (!b) return;
+  for (size_t d = 0; d < b->parts.size() && d < g_devs.size(); d++) {
+    cudaSetDevice(g_devs[d].id);
+    cudaFree(b->parts[d].proofs);
+    cudaFree(b->parts[d].inputs);
+    cudaFree(b->parts[d].status);
+  }
+  delete b;
+}
+
+// ---- synthetic workloads -----------------------------------------------------------------------
+static void host_g1_mul_gen(G1Aff& out, const Fr& k_mont) {
+  Fr k = fe_from_mont(k_mont);
+  to_affine(out, scalar_mul(g1_generator(), k.v));
+}
+static void host_g2_mul_gen(G2Aff& out, const Fr& k_mont) {
+  Fr k = fe_from_mont(k_mont);
+  to_affine(out, scalar_mul(g2_generator_dev(), k.v));
+}
+
+int bn254v_groth16_synth(uint64_t seed, int n_public, int sign_mode, size_t first_index, size_t n, uint8_t* vk_bytes,
+                         size_t* vk_len, uint8_t* proofs, uint8_t* inputs_be, uint8_t* expected) {
+  if (n_public < 1 || n_public + 1 > BN_MAX_IC_SYNTH || (sign_mode != 0 && sign_mode != 1))
+    return fail(BN254V_E_BAD_ARG, "bad argument");
+  int rc = ensure_init();
+  if (rc) return rc;
+  Groth16Trapdoor td;
+  trapdoor_init(td, seed, n_public);
+  if (vk_bytes) {
+    // gnark layout: alpha1 | beta1 | beta2 | gamma2 | delta1 | delta2 | u32 |K| | K.. |
+    // u32 0 | Pedersen g, gRootSigmaNeg (parsed, unused: the G2 generator twice)
+    size_t need = 288 + 4 + 32 * (size_t)(n_public + 1) + 4 + 128;
+    if (!vk_len || *vk_len < need) return fail(BN254V_E_BAD_ARG, "vk buffer too small (%zu needed)", need);
+    G1Aff a1, b1, d1;
+    G2Aff b2, g2, d2, gen = g2_generator_dev();
+    host_g1_mul_gen(a1, td.alpha);
+    host_g1_mul_gen(b1, td.beta);
+    host_g2_mul_gen(b2, td.beta);
+    host_g2_mul_gen(g2, td.gamma);
+    host_g1_mul_gen(d1, td.delta);
+    host_g2_mul_gen(d2, td.delta);
+    uint8_t* o = vk_bytes;
+    gnark::compress_g1(o, a1);
+    gnark::compress_g1(o + 32, b1);
+    gnark::compress_g2(o + 64, b2);
+    gnark::compress_g2(o + 128, g2);
+    gnark::compress_g1(o + 192, d1);
+    gnark::compress_g2(o + 224, d2);
+    uint32_t nk = (uint32_t)(n_public + 1);
+    o[288] = (uint8_t)(nk >> 24), o[289] = (uint8_t)(nk >> 16), o[290] = (uint8_t)(nk >> 8), o[291] = (uint8_t)nk;
+    o += 292;
+    for (uint32_t i = 0; i < nk; i++, o += 32) {
+      G1Aff k;
+      host_g1_mul_gen(k, td.ic[i]);
+      gnark::compress_g1(o, k);
+    }
+    memset(o, 0, 4);
+    o += 4;
+    gnark::compress_g2(o, gen);
+    gnark::compress_g2(o + 64, gen);
+    *vk_len = need;
+  }
+  if (n == 0) return BN254V_SUCCESS;
+  if (!proofs || !inputs_be || !expected) return fail(BN254V_E_BAD_ARG, "null output buffer");
+  Dev& dev = g_devs[0];
+  CU(cudaSetDevice(dev.id));
+  DevBuf dp, di, de;
+  CU(dp.alloc(n * 256));
+  CU(di.alloc(n * 32 * n_public));
+  CU(de.alloc(n));
+  unsigned grid = (unsigned)((n + BN_TPB - 1) / BN_TPB);
+  k_groth16_synth<<<grid, BN_TPB, 0, dev.stream>>>(td, seed, first_index, n, n_public, sign_mode, dp.as<uint8_t>(),
+                                                   di.as<uint8_t>(), de.as<uint8_t>());
+  g_launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(proofs, dp.p, n * 256, cudaMemcpyDeviceToHost, dev.stream));
+  CU(cudaMemcpyAsync(inputs_be, di.p, n * 32 * n_public, cudaMemcpyDeviceToHost, dev.stream));
+  CU(cudaMemcpyAsync(expected, de.p, n, cudaMemcpyDeviceToHost, dev.stream));
+  CU(cudaStreamSynchronize(dev.stream));
+  return BN254V_SUCCESS;
+}
+
+int bn254v_pairing_synth(uint64_t seed, int k, size_t first_index, size_t n, uint8_t* g1, uint8_t* g2,
+                         uint8_t* expected_is_one) {
+  if (k < 1 || k > 4 || !g1 || !g2 || !expected_is_one) return fail(BN254V_E_BAD_ARG, "bad argument");
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (n == 0) return BN254V_SUCCESS;
+  Dev& dev = g_devs[0];
+  CU(cudaSetDevice(dev.id));
+  DevBuf d1, d2, de;
+  CU(d1.alloc(n * 64 * k));
+  CU(d2.alloc(n * 128 * k));
+  CU(de.alloc(n));
+  unsigned grid = (unsigned)((n + BN_TPB - 1) / BN_TPB);
+  k_pairing_synth<<<grid, BN_TPB, 0, dev.stream>>>(seed, first_index, n, k, d1.as<uint8_t>(), d2.as<uint8_t>(),
+                                                   de.as<uint8_t>());
+  g_launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(g1, d1.p, n * 64 * k, cudaMemcpyDeviceToHost, dev.stream));
+  CU(cudaMemcpyAsync(g2, d2.p, n * 128 * k, cudaMemcpyDeviceToHost, dev.stream));
+  CU(cudaMemcpyAsync(expected_is_one, de.p, n, cudaMemcpyDeviceToHost, dev.stream));
+  CU(cudaStreamSynchronize(dev.stream));
+  return BN254V_SUCCESS;
+}
+
+// ---- measurement helpers -----------------------------------------------------------------------
+int bn254v_imad_peak(int iters, double* wide_mac_per_s, double* lo_mac_per_s, float* sm_clock_mhz) {
+  if (iters < 1) return fail(BN254V_E_BAD_ARG, "iters < 1");
+  int rc = ensure_init();
+  if (rc) return rc;
+  Dev& dev = g_devs[0];
+  CU(cudaSetDevice(dev.id));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, dev.id));
+  DevBuf sink;
+  CU(sink.alloc(8));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256;
+  const double macs = (double)blocks * threads * (double)iters * 32.0;
+  float ms;
+  for (int pass = 0; pass < 2; pass++) {  // pass 0 warms up
+    CU(cudaEventRecord(dev.ev0, dev.stream));
+    k_imad_peak<true><<<blocks, threads, 0, dev.stream>>>(iters, 12345u, 6789u, sink.as<uint64_t>());
+    CU(cudaEventRecord(dev.ev1, dev.stream));
+    CU(cudaStreamSynchronize(dev.stream));
+    CU(cudaEventElapsedTime(&ms, dev.ev0, dev.ev1));
+    g_launches++;
+  }
+  if (wide_mac_per_s) *wide_mac_per_s = macs / (ms * 1e-3);
+  for (int pass = 0; pass < 2; pass++) {
+    CU(cudaEventRecord(dev.ev0, dev.stream));
+    k_imad_peak<false><<<blocks, threads, 0, dev.stream>>>(iters, 12345u, 6789u, sink.as<uint64_t>());
+    CU(cudaEventRecord(dev.ev1, dev.stream));
+    CU(cudaStreamSynchronize(dev.stream));
+    CU(cudaEventElapsedTime(&ms, dev.ev0, dev.ev1));
+    g_launches++;
+  }
+  if (lo_mac_per_s) *lo_mac_per_s = macs / (ms * 1e-3);
+  if (sm_clock_mhz) *sm_clock_mhz = prop.clockRate / 1000.f;
+  return BN254V_SUCCESS;
+}
+
+}  // extern "C"

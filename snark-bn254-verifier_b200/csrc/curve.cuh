@@ -53,7 +53,7 @@ HD Aff<F> neg(const Aff<F>& p) {
 
 // dbl-2009-l (a = 0): 2M + 5S
 template <class F>
-HD Jac<F> jac_double(const Jac<F>& p) {
+HDN Jac<F> jac_double(const Jac<F>& p) {
   F A = sqr(p.x);
   F B = sqr(p.y);
   F C = sqr(B);
@@ -68,7 +68,7 @@ HD Jac<F> jac_double(const Jac<F>& p) {
 
 // madd-2007-bl mixed addition (q affine, not identity), complete w.r.t. p == identity, p == +-q.
 template <class F>
-HD Jac<F> jac_add_mixed(const Jac<F>& p, const Aff<F>& q) {
+HDN Jac<F> jac_add_mixed(const Jac<F>& p, const Aff<F>& q) {
   if (is_identity(p)) return to_jac(q);
   F Z1Z1 = sqr(p.z);
   F U2 = mul(q.x, Z1Z1);
@@ -92,7 +92,7 @@ HD Jac<F> jac_add_mixed(const Jac<F>& p, const Aff<F>& q) {
 
 // add-2007-bl full Jacobian addition
 template <class F>
-HD Jac<F> jac_add(const Jac<F>& p, const Jac<F>& q) {
+HDN Jac<F> jac_add(const Jac<F>& p, const Jac<F>& q) {
   if (is_identity(p)) return q;
   if (is_identity(q)) return p;
   F Z1Z1 = sqr(p.z);
@@ -119,7 +119,7 @@ HD Jac<F> jac_add(const Jac<F>& p, const Jac<F>& q) {
 
 // Returns false for the identity (substrate-bn: "Unable to convert G1 to AffineG1").
 template <class F>
-HD bool to_affine(Aff<F>& out, const Jac<F>& p) {
+HDN bool to_affine(Aff<F>& out, const Jac<F>& p) {
   if (is_identity(p)) return false;
   F zi = inv(p.z);
   F zi2 = sqr(zi);
@@ -130,7 +130,7 @@ HD bool to_affine(Aff<F>& out, const Jac<F>& p) {
 
 // MSB-first double-and-add over a 256-bit plain scalar (8 LE words).
 template <class F>
-HD Jac<F> scalar_mul(const Aff<F>& p, const uint32_t* k) {
+HDN Jac<F> scalar_mul(const Aff<F>& p, const uint32_t* k) {
   Jac<F> acc = jac_identity<F>();
   bool started = false;
   for (int i = 255; i >= 0; i--) {
@@ -153,7 +153,7 @@ HD G2Aff g2_psi(const G2Aff& q) {
   BN_LOAD_FP2(cy, K::frob1, 2);  // xi^((p-1)/2)
   return G2Aff{mul(conj(q.x), cx), mul(conj(q.y), cy)};
 }
-HD bool g2_in_subgroup(const G2Aff& q) {
+HDN bool g2_in_subgroup(const G2Aff& q) {
   // 6x^2 = 0x6f4d8248eeb859fbf83e9682e87cfd46 (127 bits).  Exactness: psi satisfies
   // psi^2 - t psi + p = 0 and gcd((6x^2)^2 - t 6x^2 + p, #E'(Fq2)/r) = 1, so the test forces ord(P) | r.
   const uint32_t k[8] = {0xe87cfd46u, 0xf83e9682u, 0xeeb859fbu, 0x6f4d8248u, 0, 0, 0, 0};

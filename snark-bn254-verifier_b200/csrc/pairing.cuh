@@ -16,7 +16,7 @@ struct Line {
 };
 
 // R <- 2R, returns the tangent line coefficients.
-HD Line doubling_step(G2Jac& r) {
+HDN Line doubling_step(G2Jac& r) {
   Fp2 a = fp2_halve(mul(r.x, r.y));
   Fp2 b = sqr(r.y);
   Fp2 c = sqr(r.z);
@@ -35,7 +35,7 @@ HD Line doubling_step(G2Jac& r) {
 }
 
 // R <- R + Q (Q affine), returns the chord line coefficients.
-HD Line addition_step(G2Jac& r, const G2Aff& q) {
+HDN Line addition_step(G2Jac& r, const G2Aff& q) {
   Fp2 d = sub(r.x, mul(r.z, q.x));
   Fp2 e = sub(r.y, mul(r.z, q.y));
   Fp2 f = sqr(d);
@@ -53,14 +53,14 @@ HD Line addition_step(G2Jac& r, const G2Aff& q) {
 HD G2Aff g2_mul_by_q(const G2Aff& q) { return g2_psi(q); }
 
 // f <- f * line(P): mul_by_024(ell_0, ell_vw * P.y, ell_vv * P.x)
-HD void apply_line(Fp12& f, const Line& l, const G1Aff& p) {
+HDN void apply_line(Fp12& f, const Line& l, const G1Aff& p) {
   f = mul_by_024(f, l.ell_0, scale(l.ell_vw, p.y), scale(l.ell_vv, p.x));
 }
 
 #define BN_N_LINES 87
 
 // G2::precompute -> 87 line triples for a fixed (VK-constant) G2 point.
-HD void g2_precompute(Line* out, const G2Aff& q) {
+HDN void g2_precompute(Line* out, const G2Aff& q) {
   G2Jac r = to_jac(q);
   G2Aff nq = neg(q);
   int idx = 0;
@@ -129,7 +129,7 @@ HD Fp12 miller_loop(const G1Aff* pv, const G2Aff* qv, const G1Aff* pf, const Lin
 }
 
 // conj(a^x), x = BN parameter, square-and-multiply with cyclotomic squarings
-HD Fp12 exp_by_neg_z(const Fp12& a) {
+HDN Fp12 exp_by_neg_z(const Fp12& a) {
   Fp12 r = a;  // leading one of x (bit 62)
   for (int i = 61; i >= 0; i--) {
     r = cyclotomic_sqr(r);
@@ -139,7 +139,7 @@ HD Fp12 exp_by_neg_z(const Fp12& a) {
 }
 
 // Fq12::final_exponentiation.  `f` must be non-zero (a Miller value always is).
-HD Fp12 final_exponentiation(const Fp12& f) {
+HDN Fp12 final_exponentiation(const Fp12& f) {
   Fp12 t = mul(conj(f), inv(f));
   t = mul(frobenius<2>(t), t);
   Fp12 a = exp_by_neg_z(t);

@@ -142,19 +142,19 @@ HD bool eq(const Fp12& a, const Fp12& b) { return eq(a.c0, b.c0) && eq(a.c1, b.c
 HD Fp12 conj(const Fp12& a) { return Fp12{a.c0, neg(a.c1)}; }  // unitary inverse
 
 // Karatsuba: 3 Fp6 multiplications
-HD Fp12 mul(const Fp12& a, const Fp12& b) {
+HDN Fp12 mul(const Fp12& a, const Fp12& b) {
   Fp6 v0 = mul(a.c0, b.c0);
   Fp6 v1 = mul(a.c1, b.c1);
   Fp6 s = mul(add(a.c0, a.c1), add(b.c0, b.c1));
   return Fp12{add(v0, mul_v(v1)), sub(sub(s, v0), v1)};
 }
 // complex squaring: 2 Fp6 multiplications
-HD Fp12 sqr(const Fp12& a) {
+HDN Fp12 sqr(const Fp12& a) {
   Fp6 ab = mul(a.c0, a.c1);
   Fp6 t = mul(add(a.c0, a.c1), add(a.c0, mul_v(a.c1)));
   return Fp12{sub(sub(t, ab), mul_v(ab)), dbl(ab)};
 }
-HD Fp12 inv(const Fp12& a) {
+HDN Fp12 inv(const Fp12& a) {
   Fp6 t = sub(sqr(a.c0), mul_v(sqr(a.c1)));
   Fp6 ti = inv(t);
   return Fp12{mul(a.c0, ti), neg(mul(a.c1, ti))};
@@ -162,7 +162,7 @@ HD Fp12 inv(const Fp12& a) {
 
 // f * (x0 + x2 v^2 + x4 v w)  -- substrate-bn's mul_by_024(ell_0 = x0, ell_vw = x4, ell_vv = x2):
 // the sparse operand is Fq12{c0: (x0, 0, x2), c1: (0, x4, 0)}.  14 Fp2 multiplications.
-HD Fp12 mul_by_024(const Fp12& f, const Fp2& x0, const Fp2& x4, const Fp2& x2) {
+HDN Fp12 mul_by_024(const Fp12& f, const Fp2& x0, const Fp2& x4, const Fp2& x2) {
   const Fp6& A = f.c0;
   const Fp6& B = f.c1;
   // A * (x0, 0, x2): 5 mul
@@ -186,7 +186,7 @@ HD void fp4_sqr(Fp2& t0, Fp2& t1, const Fp2& z0, const Fp2& z1) {
   t0 = sub(sub(mul(add(z0, z1), add(z0, mul_xi(z1))), tmp), mul_xi(tmp));
   t1 = dbl(tmp);
 }
-HD Fp12 cyclotomic_sqr(const Fp12& a) {
+HDN Fp12 cyclotomic_sqr(const Fp12& a) {
   Fp2 z0 = a.c0.c0, z4 = a.c0.c1, z3 = a.c0.c2, z2 = a.c1.c0, z1 = a.c1.c1, z5 = a.c1.c2;
   Fp2 t0, t1, t2, t3, t4, t5;
   fp4_sqr(t0, t1, z0, z1);
@@ -213,7 +213,7 @@ HD Fp2 frob_coeff(int i) {  // i = 1..5
   return r;
 }
 template <int KK>
-HD Fp12 frobenius(const Fp12& a) {
+HDN Fp12 frobenius(const Fp12& a) {
   // w-power order: a0=c0.c0, a1=c1.c0, a2=c0.c1, a3=c1.c1, a4=c0.c2, a5=c1.c2
   Fp12 r;
   if (KK & 1) {
@@ -236,7 +236,7 @@ HD Fp12 frobenius(const Fp12& a) {
 }
 
 // canonical serialisation: 12 x 32-byte BE, order c0.c0.c0, c0.c0.c1, c0.c1.c0, ..., c1.c2.c1
-HD void fp12_to_bytes(uint8_t* out, const Fp12& a) {
+HDN void fp12_to_bytes(uint8_t* out, const Fp12& a) {
   const Fp2* cs[6] = {&a.c0.c0, &a.c0.c1, &a.c0.c2, &a.c1.c0, &a.c1.c1, &a.c1.c2};
   for (int i = 0; i < 6; i++) {
     fe_to_be_bytes(out + 64 * i, fe_from_mont(cs[i]->c0));
