@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
@@ -100,7 +101,8 @@ __global__ void k_groth16_vk_prepare(Groth16VkDev* vk) {
   if (blockIdx.x == 0 && threadIdx.x == 0) groth16_vk_prepare(*vk);
 }
 
-__global__ void __launch_bounds__(BN_TPB)
+template <int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB)
     k_groth16_verify(const Groth16VkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride,
                      const uint32_t* __restrict__ proof_len, const uint8_t* __restrict__ inputs, int n_inputs,
                      size_t n, uint8_t* __restrict__ status, uint8_t* dbg_l, uint8_t* dbg_m, uint8_t* dbg_gt) {
@@ -141,6 +143,31 @@ __global__ void __launch_bounds__(BN_TPB)
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   pairing_synth_one(g1 + (size_t)64 * k * i, g2 + (size_t)128 * k * i, expected + i, seed, first + i, k);
+}
+
+// Launch-shape variants (threads per block x resident blocks per SM -> registers per thread); the default is
+// the one measured fastest on B200 (profiles/), BN254V_VARIANT overrides it for experiments.
+static void launch_groth16_verify(cudaStream_t st, const Groth16VkDev* vk, const uint8_t* proofs, size_t stride,
+                                  const uint32_t* lens, const uint8_t* inputs, int n_inputs, size_t m, uint8_t* status,
+                                  uint8_t* l, uint8_t* ml, uint8_t* gt) {
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("BN254V_VARIANT");
+    variant = e ? atoi(e) : 0;
+  }
+#define LV(TPB, MINB)                                                                                              \
+  k_groth16_verify<TPB, MINB><<<(unsigned)((m + TPB - 1) / TPB), TPB, 0, st>>>(vk, proofs, stride, lens, inputs, \
+                                                                               n_inputs, m, status, l, ml, gt)
+  switch (variant) {
+    case 1: LV(128, 3); break;
+    case 2: LV(128, 4); break;
+    case 3: LV(64, 4); break;
+    case 4: LV(64, 6); break;
+    case 5: LV(64, 8); break;
+    case 6: LV(32, 8); break;
+    default: LV(128, 2); break;
+  }
+#undef LV
 }
 
 // Dependent-free multiply-add streams: 8 independent accumulators per thread.
@@ -355,11 +382,9 @@ int bn254v_groth16_verify_batch(const bn254v_vk* vk, const uint8_t* proofs, size
     if (dbg && dbg->g1_out) CU(p.l.alloc(m * 64));
     if (dbg && dbg->miller_out) CU(p.m.alloc(m * 384));
     if (dbg && dbg->gt_out) CU(p.gt.alloc(m * 384));
-    unsigned grid = (unsigned)((m + BN_TPB - 1) / BN_TPB);
-    k_groth16_verify<<<grid, BN_TPB, 0, dev.stream>>>((const Groth16VkDev*)vk->dev[d], p.proofs.as<uint8_t>(),
-                                                      proof_stride, proof_len ? p.lens.as<uint32_t>() : nullptr,
-                                                      p.inputs.as<uint8_t>(), n_inputs, m, p.status.as<uint8_t>(),
-                                                      p.l.as<uint8_t>(), p.m.as<uint8_t>(), p.gt.as<uint8_t>());
+    launch_groth16_verify(dev.stream, (const Groth16VkDev*)vk->dev[d], p.proofs.as<uint8_t>(), proof_stride,
+                          proof_len ? p.lens.as<uint32_t>() : nullptr, p.inputs.as<uint8_t>(), n_inputs, m,
+                          p.status.as<uint8_t>(), p.l.as<uint8_t>(), p.m.as<uint8_t>(), p.gt.as<uint8_t>());
     g_launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(status + lo, p.status.p, m, cudaMemcpyDeviceToHost, dev.stream));
@@ -483,9 +508,8 @@ int bn254v_groth16_batch_verify(const bn254v_vk* vk, bn254v_batch* b, uint8_t* s
     CU(cudaSetDevice(dev.id));
     CU(cudaEventRecord(dev.ev0, dev.stream));
     if (m) {
-      unsigned grid = (unsigned)((m + BN_TPB - 1) / BN_TPB);
-      k_groth16_verify<<<grid, BN_TPB, 0, dev.stream>>>((const Groth16VkDev*)vk->dev[d], p.proofs, 256, nullptr,
-                                                        p.inputs, b->n_inputs, m, p.status, nullptr, nullptr, nullptr);
+      launch_groth16_verify(dev.stream, (const Groth16VkDev*)vk->dev[d], p.proofs, 256, nullptr, p.inputs,
+                            b->n_inputs, m, p.status, nullptr, nullptr, nullptr);
       g_launches++;
       CU(cudaGetLastError());
     }

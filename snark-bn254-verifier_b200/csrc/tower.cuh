@@ -51,22 +51,22 @@ HD Fp2 conj(const Fp2& a) { return Fp2{a.c0, fe_neg(a.c1)}; }
 HD bool is_zero(const Fp2& a) { return fe_is_zero(a.c0) && fe_is_zero(a.c1); }
 HD bool eq(const Fp2& a, const Fp2& b) { return fe_eq(a.c0, b.c0) && fe_eq(a.c1, b.c1); }
 
-// Karatsuba: 3 base multiplications
-HD Fp2 mul(const Fp2& a, const Fp2& b) {
+// Karatsuba: 3 base multiplications.  Out of line, operands by value (registers): one copy in the binary.
+HDN Fp2 mul(Fp2 a, Fp2 b) {
   Fp t0 = fe_mul(a.c0, b.c0);
   Fp t1 = fe_mul(a.c1, b.c1);
   Fp s = fe_mul(fe_add(a.c0, a.c1), fe_add(b.c0, b.c1));
   return Fp2{fe_sub(t0, t1), fe_sub(fe_sub(s, t0), t1)};
 }
 // (a0+a1)(a0-a1), 2 a0 a1
-HD Fp2 sqr(const Fp2& a) {
+HDN Fp2 sqr(Fp2 a) {
   Fp t = fe_mul(a.c0, a.c1);
   Fp c0 = fe_mul(fe_add(a.c0, a.c1), fe_sub(a.c0, a.c1));
   return Fp2{c0, fe_dbl(t)};
 }
 HD Fp2 scale(const Fp2& a, const Fp& k) { return Fp2{fe_mul(a.c0, k), fe_mul(a.c1, k)}; }
 // multiply by xi = 9 + u: (9 a0 - a1) + (a0 + 9 a1) u
-HD Fp2 mul_xi(const Fp2& a) {
+HDN Fp2 mul_xi(Fp2 a) {
   Fp t0 = fe_dbl(fe_dbl(fe_dbl(a.c0)));  // 8 a0
   Fp t1 = fe_dbl(fe_dbl(fe_dbl(a.c1)));  // 8 a1
   return Fp2{fe_sub(fe_add(t0, a.c0), a.c1), fe_add(fe_add(t1, a.c1), a.c0)};
@@ -104,7 +104,7 @@ HD bool eq(const Fp6& a, const Fp6& b) { return eq(a.c0, b.c0) && eq(a.c1, b.c1)
 HD Fp6 mul_v(const Fp6& a) { return Fp6{mul_xi(a.c2), a.c0, a.c1}; }
 
 // Karatsuba: 6 Fp2 multiplications
-HD Fp6 mul(const Fp6& a, const Fp6& b) {
+HDN Fp6 mul(const Fp6& a, const Fp6& b) {
   Fp2 v0 = mul(a.c0, b.c0);
   Fp2 v1 = mul(a.c1, b.c1);
   Fp2 v2 = mul(a.c2, b.c2);
@@ -114,7 +114,7 @@ HD Fp6 mul(const Fp6& a, const Fp6& b) {
   return Fp6{add(v0, mul_xi(t0)), add(t1, mul_xi(v2)), add(t2, v1)};
 }
 // CH-SQR2: 2 mul + 3 sqr in Fp2
-HD Fp6 sqr(const Fp6& a) {
+HDN Fp6 sqr(const Fp6& a) {
   Fp2 s0 = sqr(a.c0);
   Fp2 ab = mul(a.c0, a.c1);
   Fp2 s1 = dbl(ab);
@@ -124,7 +124,7 @@ HD Fp6 sqr(const Fp6& a) {
   Fp2 s4 = sqr(a.c2);
   return Fp6{add(s0, mul_xi(s3)), add(s1, mul_xi(s4)), sub(add(add(s1, s2), s3), add(s0, s4))};
 }
-HD Fp6 inv(const Fp6& a) {
+HDN Fp6 inv(const Fp6& a) {
   Fp2 c0 = sub(sqr(a.c0), mul_xi(mul(a.c1, a.c2)));
   Fp2 c1 = sub(mul_xi(sqr(a.c2)), mul(a.c0, a.c1));
   Fp2 c2 = sub(sqr(a.c1), mul(a.c0, a.c2));
