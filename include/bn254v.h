@@ -47,6 +47,7 @@ enum bn254v_status {
   BN254V_PANIC_IDENTITY = 19,        /* bn: "Unable to convert G1 to AffineG1" (identity intermediate)*/
   BN254V_PANIC_SHORT_BUFFER = 20,    /* slice index out of range                groth16/converter.rs:15 */
   BN254V_PANIC_DIV_BY_ZERO = 21,     /* Fr `/=` by zero                          plonk/verify.rs:157  */
+  BN254V_PANIC_INDEX_OUT_OF_RANGE = 22, /* claimed_values[1..5] missing           plonk/verify.rs:166-170 */
   BN254V_STATUS_UNSET = 255
 };
 

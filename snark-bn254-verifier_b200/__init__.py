@@ -28,7 +28,7 @@ OK_TRUE, OK_FALSE = 0, 1
 ERR_PREPARE_INPUTS, ERR_BSB22_MISMATCH, ERR_INVALID_WITNESS, ERR_INVERSE_NOT_FOUND = 2, 3, 4, 5
 ERR_OPENING_POLY_MISMATCH, ERR_INVALID_NUMBER_OF_DIGESTS, ERR_PAIRING_CHECK_FAILED = 6, 7, 8
 PANIC_FIELD_NOT_MEMBER, PANIC_NOT_ON_CURVE, PANIC_NOT_IN_SUBGROUP, PANIC_IDENTITY = 16, 17, 18, 19
-PANIC_SHORT_BUFFER, PANIC_DIV_BY_ZERO, STATUS_UNSET = 20, 21, 255
+PANIC_SHORT_BUFFER, PANIC_DIV_BY_ZERO, PANIC_INDEX_OUT_OF_RANGE, STATUS_UNSET = 20, 21, 22, 255
 
 E_BAD_ARG, E_NO_DEVICE, E_CUDA, E_VK_PARSE, E_UNSUPPORTED = -1, -2, -3, -4, -5
 

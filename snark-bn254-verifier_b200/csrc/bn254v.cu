@@ -15,6 +15,7 @@
 
 #include "gnark_host.h"
 #include "groth16.cuh"
+#include "plonk.cuh"
 #include "synth.cuh"
 
 using namespace bn254;
@@ -114,6 +115,25 @@ __global__ void __launch_bounds__(TPB, MINB)
   if (len > stride) len = (uint32_t)stride;
   status[i] = (uint8_t)groth16_verify_one(*vk, proofs + stride * i, len, inputs + (size_t)32 * n_inputs * i,
                                           n_inputs, dbg);
+}
+
+__global__ void k_plonk_vk_prepare(PlonkVkDev* vk) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) plonk_vk_prepare(*vk);
+}
+
+__global__ void __launch_bounds__(BN_TPB)
+    k_plonk_verify(const PlonkVkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride,
+                   const uint32_t* __restrict__ proof_len, const uint8_t* __restrict__ inputs, int n_inputs,
+                   const uint8_t* __restrict__ rnd, size_t n, uint8_t* __restrict__ status, uint8_t* dbg_g1,
+                   uint8_t* dbg_fr, uint8_t* dbg_m, uint8_t* dbg_gt) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  PlonkDebug dbg{dbg_g1 ? dbg_g1 + 256 * i : nullptr, dbg_fr ? dbg_fr + 256 * i : nullptr,
+                 dbg_m ? dbg_m + 384 * i : nullptr, dbg_gt ? dbg_gt + 384 * i : nullptr};
+  uint32_t len = proof_len ? proof_len[i] : (uint32_t)stride;
+  if (len > stride) len = (uint32_t)stride;
+  status[i] = (uint8_t)plonk_verify_one(*vk, proofs + stride * i, len, inputs + (size_t)32 * n_inputs * i, n_inputs,
+                                        rnd + 32 * i, dbg);
 }
 
 template <int KP>
@@ -276,6 +296,7 @@ const char* bn254v_status_name(int s) {
     case BN254V_PANIC_IDENTITY: return "PANIC_IDENTITY";
     case BN254V_PANIC_SHORT_BUFFER: return "PANIC_SHORT_BUFFER";
     case BN254V_PANIC_DIV_BY_ZERO: return "PANIC_DIV_BY_ZERO";
+    case BN254V_PANIC_INDEX_OUT_OF_RANGE: return "PANIC_INDEX_OUT_OF_RANGE";
     case BN254V_STATUS_UNSET: return "UNSET";
   }
   return "?";
@@ -328,10 +349,69 @@ int bn254v_groth16_vk_load(const uint8_t* vk_bytes, size_t len, int sign_mode, b
 }
 
 int bn254v_plonk_vk_load(const uint8_t* vk_bytes, size_t len, bn254v_vk** out) {
-  (void)vk_bytes;
-  (void)len;
-  (void)out;
-  return fail(BN254V_E_UNSUPPORTED, "PlonK path not built yet");
+  if (!vk_bytes || !out) return fail(BN254V_E_BAD_ARG, "bad argument");
+  int rc = ensure_init();
+  if (rc) return rc;
+  gnark::PlonkVkHost h;
+  if (gnark::parse_plonk_vk(h, vk_bytes, len)) return fail(BN254V_E_VK_PARSE, "malformed PlonK VK");
+  if (h.qcp.size() > BN_MAX_QCP || h.cci.size() != h.qcp.size() || h.nb_public > BN_MAX_PLONK_PUBLIC)
+    return fail(BN254V_E_UNSUPPORTED, "VK shape outside compiled limits (nQcp %zu, nIdx %zu, nPublic %llu)",
+                h.qcp.size(), h.cci.size(), (unsigned long long)h.nb_public);
+  PlonkVkDev* hv = new PlonkVkDev();
+  memset(hv, 0, sizeof *hv);
+  hv->size = h.size;
+  hv->n_public = (int)h.nb_public;
+  hv->n_qcp = (int)h.qcp.size();
+  hv->size_inv = fe_to_mont(h.size_inv);
+  hv->generator = fe_to_mont(h.generator);
+  hv->coset_shift = fe_to_mont(h.coset_shift);
+  for (int i = 0; i < hv->n_qcp; i++) hv->w_pow_cci[i] = fr_pow_u64(hv->generator, h.nb_public + h.cci[i]);
+  for (int i = 0; i < 3; i++) hv->s[i] = h.s[i];
+  hv->ql = h.ql, hv->qr = h.qr, hv->qm = h.qm, hv->qo = h.qo, hv->qk = h.qk, hv->g1 = h.g1;
+  hv->g2[0] = h.g2[0], hv->g2[1] = h.g2[1];
+  for (int i = 0; i < hv->n_qcp; i++) hv->qcp[i] = h.qcp[i];
+  {  // "gamma" | S1 S2 S3 Ql Qr Qm Qo Qk | Qcp..  (bind_public_data, verifier/src/plonk/verify.rs:325-335)
+    sha256_init(hv->gamma_prefix);
+    sha_bytes(hv->gamma_prefix, "gamma", 5);
+    const G1Aff* pts[8] = {&hv->s[0], &hv->s[1], &hv->s[2], &hv->ql, &hv->qr, &hv->qm, &hv->qo, &hv->qk};
+    uint8_t b[64];
+    for (int i = 0; i < 8; i++) {
+      store_g1(b, *pts[i]);
+      sha256_update(hv->gamma_prefix, b, 64);
+    }
+    for (int i = 0; i < hv->n_qcp; i++) {
+      store_g1(b, hv->qcp[i]);
+      sha256_update(hv->gamma_prefix, b, 64);
+    }
+    store_g1(hv->kzg_vk_bytes, hv->s[0]);
+    store_g1(hv->kzg_vk_bytes + 64, hv->s[1]);
+    for (int i = 0; i < hv->n_qcp; i++) store_g1(hv->kzg_vk_bytes + 128 + 64 * i, hv->qcp[i]);
+  }
+  bn254v_vk* vk = new bn254v_vk();
+  vk->kind = 1;
+  vk->n_public = hv->n_public;
+  vk->sign_mode = 0;
+  for (auto& d : g_devs) {
+    cudaError_t e = cudaSetDevice(d.id);
+    PlonkVkDev* dv = nullptr;
+    if (e == cudaSuccess) e = cudaMalloc(&dv, sizeof(PlonkVkDev));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dv, hv, sizeof(PlonkVkDev), cudaMemcpyHostToDevice, d.stream);
+    if (e == cudaSuccess) {
+      k_plonk_vk_prepare<<<1, 32, 0, d.stream>>>(dv);
+      g_launches++;
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+    if (e != cudaSuccess) {
+      delete hv;
+      bn254v_vk_free(vk);
+      return fail(BN254V_E_CUDA, "vk upload/prepare: %s", cudaGetErrorString(e));
+    }
+    vk->dev.push_back(dv);
+  }
+  delete hv;
+  *out = vk;
+  return BN254V_SUCCESS;
 }
 
 void bn254v_vk_free(bn254v_vk* vk) {
@@ -402,9 +482,65 @@ int bn254v_groth16_verify_batch(const bn254v_vk* vk, const uint8_t* proofs, size
 int bn254v_plonk_verify_batch(const bn254v_vk* vk, const uint8_t* proofs, size_t proof_stride,
                               const uint32_t* proof_len, const uint8_t* inputs_be, int n_inputs,
                               const uint8_t* rnd_be, size_t n, uint8_t* status, const bn254v_debug* dbg) {
-  (void)vk; (void)proofs; (void)proof_stride; (void)proof_len; (void)inputs_be; (void)n_inputs;
-  (void)rnd_be; (void)n; (void)status; (void)dbg;
-  return fail(BN254V_E_UNSUPPORTED, "PlonK path not built yet");
+  if (!vk || vk->kind != 1 || !status || (n && (!proofs || !rnd_be || (n_inputs > 0 && !inputs_be))) || n_inputs < 0 ||
+      n_inputs > BN_MAX_PLONK_PUBLIC)
+    return fail(BN254V_E_BAD_ARG, "bad argument");
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (n == 0) return BN254V_SUCCESS;
+  const int nd = (int)g_devs.size();
+  struct Part {
+    DevBuf proofs, lens, inputs, rnd, status, g1, fr, m, gt;
+  };
+  std::vector<Part> parts(nd);
+  const size_t in_bytes = (size_t)32 * n_inputs;
+  for (int d = 0; d < nd; d++) {
+    size_t lo, hi;
+    shard(n, d, nd, lo, hi);
+    size_t m = hi - lo;
+    if (!m) continue;
+    Part& p = parts[d];
+    Dev& dev = g_devs[d];
+    CU(cudaSetDevice(dev.id));
+    CU(p.proofs.alloc(m * proof_stride));
+    CU(p.inputs.alloc(m * in_bytes));
+    CU(p.rnd.alloc(m * 32));
+    CU(p.status.alloc(m));
+    CU(cudaMemcpyAsync(p.proofs.p, proofs + lo * proof_stride, m * proof_stride, cudaMemcpyHostToDevice, dev.stream));
+    if (in_bytes)
+      CU(cudaMemcpyAsync(p.inputs.p, inputs_be + lo * in_bytes, m * in_bytes, cudaMemcpyHostToDevice, dev.stream));
+    CU(cudaMemcpyAsync(p.rnd.p, rnd_be + lo * 32, m * 32, cudaMemcpyHostToDevice, dev.stream));
+    if (proof_len) {
+      CU(p.lens.alloc(m * 4));
+      CU(cudaMemcpyAsync(p.lens.p, proof_len + lo, m * 4, cudaMemcpyHostToDevice, dev.stream));
+    }
+    if (dbg && dbg->g1_out) CU(p.g1.alloc(m * 256));
+    if (dbg && dbg->fr_out) CU(p.fr.alloc(m * 256));
+    if (dbg && dbg->miller_out) CU(p.m.alloc(m * 384));
+    if (dbg && dbg->gt_out) CU(p.gt.alloc(m * 384));
+    if (p.g1.p) CU(cudaMemsetAsync(p.g1.p, 0, m * 256, dev.stream));
+    if (p.fr.p) CU(cudaMemsetAsync(p.fr.p, 0, m * 256, dev.stream));
+    if (p.m.p) CU(cudaMemsetAsync(p.m.p, 0, m * 384, dev.stream));
+    if (p.gt.p) CU(cudaMemsetAsync(p.gt.p, 0, m * 384, dev.stream));
+    unsigned grid = (unsigned)((m + BN_TPB - 1) / BN_TPB);
+    k_plonk_verify<<<grid, BN_TPB, 0, dev.stream>>>((const PlonkVkDev*)vk->dev[d], p.proofs.as<uint8_t>(), proof_stride,
+                                                    proof_len ? p.lens.as<uint32_t>() : nullptr, p.inputs.as<uint8_t>(),
+                                                    n_inputs, p.rnd.as<uint8_t>(), m, p.status.as<uint8_t>(),
+                                                    p.g1.as<uint8_t>(), p.fr.as<uint8_t>(), p.m.as<uint8_t>(),
+                                                    p.gt.as<uint8_t>());
+    g_launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(status + lo, p.status.p, m, cudaMemcpyDeviceToHost, dev.stream));
+    if (p.g1.p) CU(cudaMemcpyAsync(dbg->g1_out + lo * 256, p.g1.p, m * 256, cudaMemcpyDeviceToHost, dev.stream));
+    if (p.fr.p) CU(cudaMemcpyAsync(dbg->fr_out + lo * 256, p.fr.p, m * 256, cudaMemcpyDeviceToHost, dev.stream));
+    if (p.m.p) CU(cudaMemcpyAsync(dbg->miller_out + lo * 384, p.m.p, m * 384, cudaMemcpyDeviceToHost, dev.stream));
+    if (p.gt.p) CU(cudaMemcpyAsync(dbg->gt_out + lo * 384, p.gt.p, m * 384, cudaMemcpyDeviceToHost, dev.stream));
+  }
+  for (int d = 0; d < nd; d++) {
+    CU(cudaSetDevice(g_devs[d].id));
+    CU(cudaStreamSynchronize(g_devs[d].stream));
+  }
+  return BN254V_SUCCESS;
 }
 
 // ---- raw pairing products ----------------------------------------------------------------------

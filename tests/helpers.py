@@ -66,5 +66,59 @@ def build_hostsim():
     csrc = os.path.join(ROOT, "snark-bn254-verifier_b200", "csrc")
     deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc)]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, src], check=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-DBN254_COUNT_MULS", "-shared", "-fPIC", "-o", so, src], check=True)
     return ctypes.CDLL(so)
+
+
+PLONK_STATUS = {"OK_TRUE": 0, "ERR_BSB22_MISMATCH": 3, "ERR_INVALID_WITNESS": 4, "ERR_INVERSE_NOT_FOUND": 5,
+                "ERR_OPENING_POLY_MISMATCH": 6, "ERR_INVALID_NUMBER_OF_DIGESTS": 7, "ERR_PAIRING_CHECK_FAILED": 8,
+                "PANIC_FIELD_NOT_MEMBER": 16, "PANIC_NOT_ON_CURVE": 17, "PANIC_IDENTITY": 19, "PANIC_SHORT_BUFFER": 20,
+                "PANIC_DIV_BY_ZERO": 21, "PANIC_INDEX": 22}
+# oracle exception kinds -> status names of include/bn254v.h
+_PLONK_ERR = {"BSB22_COMMITMENT_MISMATCH": "ERR_BSB22_MISMATCH", "INVALID_WITNESS": "ERR_INVALID_WITNESS",
+              "INVERSE_NOT_FOUND": "ERR_INVERSE_NOT_FOUND", "OPENING_POLY_MISMATCH": "ERR_OPENING_POLY_MISMATCH",
+              "INVALID_NUMBER_OF_DIGESTS": "ERR_INVALID_NUMBER_OF_DIGESTS", "PAIRING_CHECK_FAILED": "ERR_PAIRING_CHECK_FAILED"}
+
+
+def oracle_plonk_status(pb, vk, xs, rnd=0x1234567):
+    import plonk_oracle as po
+    try:
+        po.plonk_verifier_verify(pb, vk, xs, rnd=rnd)
+        return "OK_TRUE"
+    except po.PlonkError as e:
+        return _PLONK_ERR[e.kind]
+    except bo.PanicError as e:
+        return "PANIC_" + e.kind
+
+
+def plonk_fixture(prog):
+    fx = load_json("fixtures.json")[f"{prog}_plonk"]
+    return bytes.fromhex(fx["raw_proof"]), [int(s) for s in fx["inputs"]]
+
+
+def plonk_vk_bytes():
+    return open(os.path.join(GOLDEN, "plonk_vk.bin"), "rb").read()
+
+
+def plonk_structural_suite(prog="fibonacci"):
+    """Framing-level edge cases of load_plonk_proof_from_bytes / verify_plonk shape checks:
+    (name, proof bytes, inputs)."""
+    raw, xs = plonk_fixture(prog)
+    out = [("valid", raw, xs)]
+    out.append(("short<516", raw[:515], xs))
+    out.append(("short claimed", raw[:516 + 40], xs))
+    out.append(("short tail", raw[:-1], xs))
+    b = bytearray(raw); b[512:516] = (5).to_bytes(4, "big")
+    out.append(("5 claimed then garbage", bytes(b), xs))
+    out.append(("one public input", raw, xs[:1]))
+    out.append(("three public inputs", raw, xs + [7]))
+    # no BSB22 commitment: nb = 0 and the 64 commitment bytes removed
+    off = 516 + 32 * 7 + 96
+    b = bytearray(raw[:off]) + (0).to_bytes(4, "big")
+    out.append(("no bsb22 commitment", bytes(b), xs))
+    b = bytearray(raw); b[off + 4 + 63] ^= 1
+    out.append(("bsb22 off curve", bytes(b), xs))
+    b = bytearray(raw); b[516 + 32 * 7 + 64:516 + 32 * 7 + 96] = bo.R.to_bytes(32, "big")
+    out.append(("zu == r", bytes(b), xs))
+    out.append(("trailing bytes", raw + bytes(40), xs))
+    return out

@@ -64,3 +64,66 @@ int hs_groth16_verify(void* vk, const uint8_t* proof, uint32_t proof_len, const 
   return groth16_verify_one(*(Groth16VkDev*)vk, proof, proof_len, inputs, n_inputs, dbg);
 }
 }
+
+// ---- PlonK (host build of plonk.cuh) ------------------------------------------------------------
+#include "../../snark-bn254-verifier_b200/csrc/gnark_host.h"
+#include "../../snark-bn254-verifier_b200/csrc/plonk.cuh"
+
+extern "C" {
+void* hs_plonk_vk_new(const uint8_t* vk_bytes, size_t len) {
+  gnark::PlonkVkHost h;
+  if (gnark::parse_plonk_vk(h, vk_bytes, len)) return nullptr;
+  PlonkVkDev* hv = new PlonkVkDev();
+  memset(hv, 0, sizeof *hv);
+  hv->size = h.size;
+  hv->n_public = (int)h.nb_public;
+  hv->n_qcp = (int)h.qcp.size();
+  hv->size_inv = fe_to_mont(h.size_inv);
+  hv->generator = fe_to_mont(h.generator);
+  hv->coset_shift = fe_to_mont(h.coset_shift);
+  for (int i = 0; i < hv->n_qcp; i++) hv->w_pow_cci[i] = fr_pow_u64(hv->generator, h.nb_public + h.cci[i]);
+  for (int i = 0; i < 3; i++) hv->s[i] = h.s[i];
+  hv->ql = h.ql, hv->qr = h.qr, hv->qm = h.qm, hv->qo = h.qo, hv->qk = h.qk, hv->g1 = h.g1;
+  hv->g2[0] = h.g2[0], hv->g2[1] = h.g2[1];
+  for (int i = 0; i < hv->n_qcp; i++) hv->qcp[i] = h.qcp[i];
+  sha256_init(hv->gamma_prefix);
+  sha_bytes(hv->gamma_prefix, "gamma", 5);
+  const G1Aff* pts[8] = {&hv->s[0], &hv->s[1], &hv->s[2], &hv->ql, &hv->qr, &hv->qm, &hv->qo, &hv->qk};
+  uint8_t b[64];
+  for (int i = 0; i < 8; i++) {
+    store_g1(b, *pts[i]);
+    sha256_update(hv->gamma_prefix, b, 64);
+  }
+  for (int i = 0; i < hv->n_qcp; i++) {
+    store_g1(b, hv->qcp[i]);
+    sha256_update(hv->gamma_prefix, b, 64);
+  }
+  store_g1(hv->kzg_vk_bytes, hv->s[0]);
+  store_g1(hv->kzg_vk_bytes + 64, hv->s[1]);
+  for (int i = 0; i < hv->n_qcp; i++) store_g1(hv->kzg_vk_bytes + 128 + 64 * i, hv->qcp[i]);
+  plonk_vk_prepare(*hv);
+  return hv;
+}
+void hs_plonk_vk_free(void* vk) { delete (PlonkVkDev*)vk; }
+int hs_plonk_verify(void* vk, const uint8_t* proof, uint32_t len, const uint8_t* inputs, int n_inputs, const uint8_t* rnd,
+                    uint8_t* g1, uint8_t* fr, uint8_t* miller, uint8_t* gt) {
+  PlonkDebug dbg{g1, fr, miller, gt};
+  return plonk_verify_one(*(PlonkVkDev*)vk, proof, len, inputs, n_inputs, rnd, dbg);
+}
+unsigned long long hs_mul_count(int reset) {
+#ifdef BN254_COUNT_MULS
+  unsigned long long c = fe_mul_counter();
+  if (reset) fe_mul_counter() = 0;
+  return c;
+#else
+  (void)reset;
+  return 0;
+#endif
+}
+void hs_sha256(const uint8_t* data, uint32_t len, uint8_t* out) {
+  Sha256 s;
+  sha256_init(s);
+  sha256_update(s, data, len);
+  sha256_final(s, out);
+}
+}

@@ -1,0 +1,108 @@
+"""GPU parity: the CUDA PlonK path (through the C ABI) against the reference's bundled fixtures, the oracle's
+golden intermediates (challenges, PI, linearised digest, folded digest, pairing inputs, Fq12 values) and the
+mutation -> status map."""
+import numpy as np
+import pytest
+
+import bn254_oracle as bo
+from helpers import (PLONK_STATUS, load_json, oracle_plonk_status, plonk_fixture, plonk_structural_suite, plonk_vk_bytes,
+                     pt_bytes)
+
+pytestmark = pytest.mark.gpu
+PROGS = ["fibonacci", "is-prime", "sha2", "tendermint"]
+
+
+def test_bundled_fixtures_verify_true(gpu):
+    """What the reference's own test pins (examples/script/src/main.rs:182-245): Ok(true) for every bundled proof."""
+    vk = plonk_vk_bytes()
+    for prog in PROGS:
+        pr, xs = plonk_fixture(prog)
+        assert gpu.PlonkVerifier.verify(pr, vk, xs) is True
+
+
+def test_fixture_intermediates_bit_exact(gpu):
+    vk = plonk_vk_bytes()
+    gold = load_json("plonk_golden.json")
+    proofs, inputs, rnds = [], [], []
+    for prog in PROGS:
+        pr, xs = plonk_fixture(prog)
+        proofs.append(pr), inputs.append(xs), rnds.append(int(gold[prog]["rnd"], 16))
+    status, dbg = gpu.PlonkVerifier.verify_batch(proofs, vk, inputs, rnd=rnds, debug=True)
+    assert (status == gpu.OK_TRUE).all()
+    for i, prog in enumerate(PROGS):
+        g = gold[prog]
+        for j, nm in enumerate(["gamma", "beta", "alpha", "zeta", "kzg_gamma", "pi", "const_lin"]):
+            assert dbg.fr[i, j].tobytes().hex() == g[nm][2:], (prog, nm)
+        assert dbg.fr[i, 7].tobytes().hex() == g["hashed_bsb22"][0][2:]
+        assert dbg.g1[i, 0].tobytes() == pt_bytes(g["lin_digest"])
+        assert dbg.g1[i, 1].tobytes() == pt_bytes(g["folded_digest"])
+        assert dbg.g1[i, 2].tobytes() == pt_bytes(g["pair_g1"][0])
+        assert dbg.g1[i, 3].tobytes() == pt_bytes(g["pair_g1"][1])
+        assert dbg.miller[i].tobytes().hex() == g["miller"] and dbg.gt[i].tobytes().hex() == g["gt"]
+
+
+def test_mutation_status_map(gpu):
+    """All 96 committed mutated proofs (4 programs x 24 classes) in one batch."""
+    vk = plonk_vk_bytes()
+    muts = load_json("plonk_mutations.json")
+    status = gpu.PlonkVerifier.verify_batch([bytes.fromhex(m["raw_proof"]) for m in muts], vk,
+                                            [[int(s) for s in m["inputs"]] for m in muts], rnd=[77] * len(muts))
+    for m, st in zip(muts, status):
+        assert st == PLONK_STATUS[m["status"]], (m["program"], m["mutation"], gpu.status_name(st))
+
+
+def test_error_semantics_single_verify(gpu):
+    """PlonkVerifier::verify never returns Ok(false): it is True or an error (verifier/src/plonk/verify.rs:316)."""
+    vk = plonk_vk_bytes()
+    by = {(m["program"], m["mutation"]): m for m in load_json("plonk_mutations.json")}
+    m = by[("sha2", "claimed0+1")]
+    with pytest.raises(gpu.PlonkError) as e:
+        gpu.PlonkVerifier.verify(bytes.fromhex(m["raw_proof"]), vk, [int(s) for s in m["inputs"]])
+    assert e.value.kind == "OpeningPolyMismatch"
+    m = by[("sha2", "batchedH*2")]
+    with pytest.raises(gpu.PlonkError) as e:
+        gpu.PlonkVerifier.verify(bytes.fromhex(m["raw_proof"]), vk, [int(s) for s in m["inputs"]])
+    assert e.value.kind == "PairingCheckFailed"
+    m = by[("sha2", "L-offcurve")]
+    with pytest.raises(gpu.VerifierPanic):
+        gpu.PlonkVerifier.verify(bytes.fromhex(m["raw_proof"]), vk, [int(s) for s in m["inputs"]])
+
+
+def test_structural_edge_cases_ragged_batch(gpu):
+    vk = plonk_vk_bytes()
+    suite = [c for c in plonk_structural_suite() if len(c[2]) == 2]
+    status = gpu.PlonkVerifier.verify_batch([c[1] for c in suite], vk, [c[2] for c in suite], rnd=[5] * len(suite))
+    for (name, pr, xs), st in zip(suite, status):
+        assert gpu.status_name(st).replace("_OUT_OF_RANGE", "") == oracle_plonk_status(pr, vk, xs), name
+    # wrong number of public inputs -> Err(InvalidWitness)
+    pr, xs = plonk_fixture("fibonacci")
+    for bad_inputs in (xs[:1], xs + [7]):
+        with pytest.raises(gpu.PlonkError) as e:
+            gpu.PlonkVerifier.verify(pr, vk, bad_inputs)
+        assert e.value.kind == "InvalidWitness"
+
+
+def test_verdict_independent_of_rnd_but_points_are_not(gpu):
+    vk = plonk_vk_bytes()
+    pr, xs = plonk_fixture("tendermint")
+    rnds = [1, 2, bo.R - 1, 0xDEADBEEF, 0x1234567, (1 << 256) - 1]
+    status, dbg = gpu.PlonkVerifier.verify_batch([pr] * len(rnds), vk, [xs] * len(rnds), rnd=rnds, debug=True)
+    assert (status == gpu.OK_TRUE).all()
+    assert len({dbg.g1[i, 2].tobytes() for i in range(len(rnds))}) == len(rnds)
+    # same values as the oracle for one of them
+    import plonk_oracle as po
+    d = {}
+    po.plonk_verifier_verify(pr, vk, xs, rnd=0x1234567, debug=d)
+    assert bo.g1_to_bytes(d["pair_g1"][0]) == dbg.g1[4, 2].tobytes()
+    assert bo.fp12_to_bytes(d["gt"]) == dbg.gt[4].tobytes()
+
+
+def test_full_size_batch_config3(gpu):
+    """BASELINE configs[2]: 2^14 proofs = bundled fixtures replicated, 50 % mutated; every status as expected."""
+    import workloads
+    n = 1 << 14
+    proofs, inputs, rnd, expected = workloads.plonk_workload(n, seed=3)
+    status = gpu.PlonkVerifier.verify_batch(proofs, plonk_vk_bytes(), inputs, rnd=rnd)
+    assert (status == expected).all()
+    assert int((status == gpu.OK_TRUE).sum()) == n // 2
+    assert {int(s) for s in np.unique(status)} == {0, 6, 8}

@@ -98,3 +98,61 @@ def test_groth16_malformed_classes(hs, pkg):
     pb, xs, _ = td.proof(0, corrupt=False)
     st = hs.hs_groth16_verify(vk, pb, 256, int(xs[0]).to_bytes(32, "big"), 1, None, None, None)
     assert st == names["ERR_PREPARE_INPUTS"]
+
+
+# ------------------------------------------------------------------------------------------------ PlonK
+def _hs_plonk(hs):
+    hs.hs_plonk_vk_new.restype = ctypes.c_void_p
+    hs.hs_plonk_vk_new.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+    hs.hs_plonk_vk_free.argtypes = [ctypes.c_void_p]
+    hs.hs_plonk_verify.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_int,
+                                   ctypes.c_char_p] + [ctypes.c_char_p] * 4
+    from helpers import plonk_vk_bytes
+    vkb = plonk_vk_bytes()
+    return hs.hs_plonk_vk_new(vkb, len(vkb))
+
+
+def test_sha256_known_answers(hs):
+    import hashlib
+    out = ctypes.create_string_buffer(32)
+    for m in (b"", b"abc", b"a" * 55, b"a" * 56, b"a" * 64, bytes(range(256)) * 5):
+        hs.hs_sha256(m, len(m), out)
+        assert out.raw == hashlib.sha256(m).digest()
+
+
+def test_plonk_fixtures_bit_exact(hs):
+    """The 4 bundled proofs: verdict Ok(true) (what the reference's test_programs pins) and every intermediate."""
+    from helpers import plonk_fixture
+    vk = _hs_plonk(hs)
+    gold = load_json("plonk_golden.json")
+    for prog, g in gold.items():
+        pr, xs = plonk_fixture(prog)
+        inputs = b"".join(x.to_bytes(32, "big") for x in xs)
+        g1, fr, ml, gt = (ctypes.create_string_buffer(n) for n in (256, 256, 384, 384))
+        st = hs.hs_plonk_verify(vk, pr, len(pr), inputs, 2, int(g["rnd"], 16).to_bytes(32, "big"), g1, fr, ml, gt)
+        assert st == 0
+        for i, nm in enumerate(["gamma", "beta", "alpha", "zeta", "kzg_gamma", "pi", "const_lin"]):
+            assert fr.raw[32 * i:32 * i + 32].hex() == g[nm][2:], nm
+        assert fr.raw[224:256].hex() == g["hashed_bsb22"][0][2:]
+        assert g1.raw[0:64] == pt_bytes(g["lin_digest"]) and g1.raw[64:128] == pt_bytes(g["folded_digest"])
+        assert g1.raw[128:192] == pt_bytes(g["pair_g1"][0]) and g1.raw[192:256] == pt_bytes(g["pair_g1"][1])
+        assert ml.raw.hex() == g["miller"] and gt.raw.hex() == g["gt"]
+    hs.hs_plonk_vk_free(vk)
+
+
+def test_plonk_mutations_and_structural_cases(hs):
+    from helpers import PLONK_STATUS, oracle_plonk_status, plonk_structural_suite, plonk_vk_bytes
+    vk = _hs_plonk(hs)
+    rnd = (0x1234567).to_bytes(32, "big")
+    for m in load_json("plonk_mutations.json"):
+        pr = bytes.fromhex(m["raw_proof"])
+        inputs = b"".join(int(s).to_bytes(32, "big") for s in m["inputs"])
+        st = hs.hs_plonk_verify(vk, pr, len(pr), inputs, 2, rnd, None, None, None, None)
+        assert st == PLONK_STATUS[m["status"]], (m["program"], m["mutation"])
+    vkb = plonk_vk_bytes()
+    for name, pr, xs in plonk_structural_suite():
+        want = oracle_plonk_status(pr, vkb, xs)
+        inputs = b"".join(int(x).to_bytes(32, "big") for x in xs)
+        st = hs.hs_plonk_verify(vk, pr, len(pr), inputs, len(xs), rnd, None, None, None, None)
+        assert st == PLONK_STATUS[want], (name, want, st)
+    hs.hs_plonk_vk_free(vk)

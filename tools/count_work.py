@@ -1,0 +1,69 @@
+"""Counts the algorithmic work of the GPU-shaped algorithms: field multiplications executed by the kernels'
+own per-proof routines, run on the host build (tests/hostsim, -DBN254_COUNT_MULS).  One Fp/Fr multiplication =
+136 limb multiply-adds with 8 x 32-bit CIOS Montgomery (64 product + 72 reduction).  Writes profiles/workcount.json,
+which bench.py uses for `roofline.achieved`.
+Run: python tools/count_work.py
+"""
+import ctypes
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def main(write=True):
+    import bn254_oracle as bo
+    from helpers import build_hostsim, load_json, plonk_fixture, plonk_vk_bytes
+    hs = build_hostsim()
+    hs.hs_mul_count.restype = ctypes.c_ulonglong
+    hs.hs_groth16_vk_new.restype = ctypes.c_void_p
+    hs.hs_groth16_verify.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_int,
+                                     ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]
+    hs.hs_plonk_vk_new.restype = ctypes.c_void_p
+    hs.hs_plonk_vk_new.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+    hs.hs_plonk_verify.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_int,
+                                   ctypes.c_char_p] + [ctypes.c_char_p] * 4
+    out = {"macs_per_mul": 136, "unit": "field multiplications per proof (Fp and Fr), counted on the host build of the "
+                                        "kernels' per-proof routines"}
+    # Groth16: mean over 8 trapdoor proofs (valid and corrupted cost the same)
+    case = load_json("groth16_golden.json")["cases"][0]
+    vk = bo.load_groth16_verifying_key_from_bytes(bytes.fromhex(case["vk"]))
+    blob = bo.g1_to_bytes(vk["alpha"]) + bo.g2_to_bytes(vk["beta2"]) + bo.g2_to_bytes(vk["gamma2"]) + \
+        bo.g2_to_bytes(bo.g2_neg(vk["delta2"])) + b"".join(bo.g1_to_bytes(k) for k in vk["k"])
+    h = hs.hs_groth16_vk_new(blob, len(vk["k"]))
+    hs.hs_mul_count(1)
+    n = 0
+    for pr in case["proofs"]:
+        inputs = b"".join(int(x).to_bytes(32, "big") for x in pr["inputs"])
+        hs.hs_groth16_verify(h, bytes.fromhex(pr["proof"]), 256, inputs, 2, None, None, None)
+        n += 1
+    out["groth16_fp_mul"] = hs.hs_mul_count(1) // n
+    # raw pairing products
+    for c in load_json("pairing_golden.json"):
+        if c["is_one"]:
+            continue
+        hs.hs_mul_count(1)
+        hs.hs_pairing_product(c["k"], bytes.fromhex(c["g1"]), bytes.fromhex(c["g2"]), None, None)
+        out["pairing_product_k%d_fp_mul" % c["k"]] = hs.hs_mul_count(1)
+    # PlonK: full path (valid proof) and early reject
+    vkb = plonk_vk_bytes()
+    pv = hs.hs_plonk_vk_new(vkb, len(vkb))
+    pr, xs = plonk_fixture("fibonacci")
+    inputs = b"".join(x.to_bytes(32, "big") for x in xs)
+    hs.hs_mul_count(1)
+    assert hs.hs_plonk_verify(pv, pr, len(pr), inputs, 2, (77).to_bytes(32, "big"), None, None, None, None) == 0
+    out["plonk_full_path_mul"] = hs.hs_mul_count(1)
+    bad = [m for m in load_json("plonk_mutations.json") if m["program"] == "fibonacci" and m["mutation"] == "claimed0+1"][0]
+    hs.hs_plonk_verify(pv, bytes.fromhex(bad["raw_proof"]), 904, inputs, 2, (77).to_bytes(32, "big"), None, None, None, None)
+    out["plonk_early_reject_mul"] = hs.hs_mul_count(1)
+    if write:
+        json.dump(out, open(os.path.join(ROOT, "profiles", "workcount.json"), "w"), indent=1)
+    return out
+
+
+if __name__ == "__main__":
+    print(json.dumps(main(), indent=1))
