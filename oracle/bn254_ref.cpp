@@ -81,32 +81,48 @@ static const u64 P_LIMBS[4] = {0x3c208c16d87cfd47ull, 0x97816a916871ca8dull, 0xb
 static const u64 R_LIMBS[4] = {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
 static const Mod MP = make_mod(P_LIMBS), MR = make_mod(R_LIMBS);
 
-static inline void mont_mul(u64* r, const u64* a, const u64* b, const Mod& M) {
-  u64 t[6] = {0, 0, 0, 0, 0, 0};
+// CIOS Montgomery product with the modulus as compile-time constants (fully unrolled by the compiler).
+template <u64 M0, u64 M1, u64 M2, u64 M3, u64 INV>
+static inline __attribute__((always_inline)) void mont_mul_c(u64* r, const u64* a, const u64* b) {
+  const u64 m[4] = {M0, M1, M2, M3};
+  u64 t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+#pragma GCC unroll 4
   for (int i = 0; i < 4; i++) {
-    u64 c = 0;
-    for (int j = 0; j < 4; j++) {
-      u128 x = (u128)a[j] * b[i] + t[j] + c;
-      t[j] = (u64)x;
-      c = (u64)(x >> 64);
-    }
-    u128 y = (u128)t[4] + c;
-    t[4] = (u64)y;
-    t[5] = (u64)(y >> 64);
-    u64 q = t[0] * M.inv;
-    u128 x = (u128)q * M.m[0] + t[0];
-    c = (u64)(x >> 64);
-    for (int j = 1; j < 4; j++) {
-      x = (u128)q * M.m[j] + t[j] + c;
-      t[j - 1] = (u64)x;
-      c = (u64)(x >> 64);
-    }
-    y = (u128)t[4] + c;
-    t[3] = (u64)y;
-    t[4] = t[5] + (u64)(y >> 64);
+    const u64 bi = b[i];
+    u128 x = (u128)a[0] * bi + t0;
+    t0 = (u64)x;
+    x = (u128)a[1] * bi + t1 + (u64)(x >> 64);
+    t1 = (u64)x;
+    x = (u128)a[2] * bi + t2 + (u64)(x >> 64);
+    t2 = (u64)x;
+    x = (u128)a[3] * bi + t3 + (u64)(x >> 64);
+    t3 = (u64)x;
+    u128 y = (u128)t4 + (u64)(x >> 64);
+    t4 = (u64)y;
+    u64 t5 = (u64)(y >> 64);
+    const u64 q = t0 * INV;
+    x = (u128)q * m[0] + t0;
+    x = (u128)q * m[1] + t1 + (u64)(x >> 64);
+    t0 = (u64)x;
+    x = (u128)q * m[2] + t2 + (u64)(x >> 64);
+    t1 = (u64)x;
+    x = (u128)q * m[3] + t3 + (u64)(x >> 64);
+    t2 = (u64)x;
+    y = (u128)t4 + (u64)(x >> 64);
+    t3 = (u64)y;
+    t4 = t5 + (u64)(y >> 64);
   }
-  if (t[4] || geq(t, M.m)) sub_n(t, t, M.m);
-  memcpy(r, t, 32);
+  u64 t[4] = {t0, t1, t2, t3};
+  if (t4 || geq(t, m)) sub_n(t, t, m);
+  r[0] = t[0], r[1] = t[1], r[2] = t[2], r[3] = t[3];
+}
+static inline void mont_mul(u64* r, const u64* a, const u64* b, const Mod& M) {
+  if (&M == &MP)
+    mont_mul_c<0x3c208c16d87cfd47ull, 0x97816a916871ca8dull, 0xb85045b68181585dull, 0x30644e72e131a029ull,
+               0x87d20782e4866389ull>(r, a, b);
+  else
+    mont_mul_c<0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull,
+               0xc2e1f593efffffffull>(r, a, b);
 }
 
 struct Fp {
