@@ -81,6 +81,7 @@ struct bn254v_vk {
   int n_public;
   int sign_mode;
   std::vector<void*> dev;  // per device slot: Groth16VkDev* / PlonkVkDev*
+  std::vector<void*> aux;  // per device slot: fixed-base tables (Groth16) or null
 };
 
 struct bn254v_batch {
@@ -115,6 +116,13 @@ __global__ void __launch_bounds__(TPB, MINB)
   if (len > stride) len = (uint32_t)stride;
   status[i] = (uint8_t)groth16_verify_one(*vk, proofs + stride * i, len, inputs + (size_t)32 * n_inputs * i,
                                           n_inputs, dbg);
+}
+
+// one thread per (IC base, window): builds the fixed-base table slices in parallel (once per VK)
+__global__ void k_groth16_ic_tables(const Groth16VkDev* vk, G1Aff* table) {
+  int b = blockIdx.x, w = threadIdx.x;
+  if (w >= BN_IC_WINDOWS) return;
+  groth16_ic_table_slice(table + ((size_t)b * BN_IC_WINDOWS + w) * BN_IC_ENTRIES, vk->ic[b + 1], w);
 }
 
 __global__ void k_plonk_vk_prepare(PlonkVkDev* vk) {
@@ -185,48 +193,49 @@ static void launch_groth16_verify(cudaStream_t st, const Groth16VkDev* vk, const
     case 4: LV(64, 6); break;
     case 5: LV(64, 8); break;
     case 6: LV(32, 8); break;
+    case 7: LV(448, 1); break;
+    case 8: LV(512, 1); break;
+    case 9: LV(256, 2); break;
+    case 10: LV(256, 1); break;
+    case 11: LV(384, 1); break;
     default: LV(128, 2); break;
   }
 #undef LV
 }
 
-// Dependent-free multiply-add streams: 8 independent accumulators per thread.
+// Integer multiply-add issue-rate probe: 8 independent chains per thread, 8 warps per SMSP.  Each step is one
+// IMAD.WIDE.U32 with a 64-bit accumulate (written as the mad.lo.cc / madc.hi pair ptxas fuses, exactly as in fe_mul)
+// or one 32-bit IMAD, plus one LOP3 on the ALU pipe that refreshes the multiplicand so that ptxas can neither hoist
+// nor strength-reduce the products (SASS checked: 32 IMAD.WIDE.U32 / IMAD + 32 LOP3 per unrolled iteration).
 template <bool WIDE>
 __global__ void __launch_bounds__(256) k_imad_peak(int iters, uint32_t a0, uint32_t b0, uint64_t* sink) {
-  uint32_t a = a0 + threadIdx.x, b = b0 + blockIdx.x;
-  if (WIDE) {
-    uint64_t acc[8];
+  uint32_t a = a0 + threadIdx.x;
+  uint32_t lo[8], hi[8], x[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) acc[j] = j;
-    for (int it = 0; it < iters; it++) {
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-#pragma unroll
-        for (int j = 0; j < 8; j++)
-          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a), "r"(b));
-      }
-    }
-    uint64_t s = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) s ^= acc[j];
-    if (s == 0x123456789abcdefull) sink[0] = s;
-  } else {
-    uint32_t acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) acc[j] = j;
-    for (int it = 0; it < iters; it++) {
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-#pragma unroll
-        for (int j = 0; j < 8; j++)
-          asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[j]) : "r"(a), "r"(b));
-      }
-    }
-    uint32_t s = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) s ^= acc[j];
-    if (s == 0x12345678u) sink[0] = s;
+  for (int j = 0; j < 8; j++) {
+    lo[j] = blockIdx.x;
+    hi[j] = b0 + j;
+    x[j] = j + a;
   }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        if (WIDE)
+          asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;"
+                       : "+r"(lo[j]), "+r"(hi[j])
+                       : "r"(x[j]), "r"(a));
+        else
+          asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[j]) : "r"(x[j]), "r"(a));
+        x[j] ^= lo[j];
+      }
+    }
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) s ^= lo[j] ^ hi[j];
+  if (s == 0x12345678u) sink[0] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -329,12 +338,22 @@ int bn254v_groth16_vk_load(const uint8_t* vk_bytes, size_t len, int sign_mode, b
     cudaError_t e = cudaSetDevice(d.id);
     Groth16VkDev* dv = nullptr;
     if (e == cudaSuccess) e = cudaMalloc(&dv, sizeof(Groth16VkDev));
+    G1Aff* table = nullptr;
+    const int n_bases = hv->n_ic - 1;
+    if (e == cudaSuccess && n_bases > 0)
+      e = cudaMalloc(&table, sizeof(G1Aff) * (size_t)n_bases * BN_IC_WINDOWS * BN_IC_ENTRIES);
+    hv->ic_table = table;
     if (e == cudaSuccess) e = cudaMemcpyAsync(dv, hv, sizeof(Groth16VkDev), cudaMemcpyHostToDevice, d.stream);
     if (e == cudaSuccess) {
       k_groth16_vk_prepare<<<1, 32, 0, d.stream>>>(dv);
       g_launches++;
+      if (n_bases > 0) {
+        k_groth16_ic_tables<<<n_bases, BN_IC_WINDOWS, 0, d.stream>>>(dv, table);
+        g_launches++;
+      }
       e = cudaGetLastError();
     }
+    vk->aux.push_back(table);
     if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
     if (e != cudaSuccess) {
       delete hv;
@@ -419,6 +438,7 @@ void bn254v_vk_free(bn254v_vk* vk) {
   for (size_t i = 0; i < vk->dev.size() && i < g_devs.size(); i++) {
     cudaSetDevice(g_devs[i].id);
     cudaFree(vk->dev[i]);
+    if (i < vk->aux.size() && vk->aux[i]) cudaFree(vk->aux[i]);
   }
   delete vk;
 }

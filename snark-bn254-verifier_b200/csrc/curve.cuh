@@ -129,11 +129,12 @@ HDN bool to_affine(Aff<F>& out, const Jac<F>& p) {
 }
 
 // MSB-first double-and-add over a 256-bit plain scalar (8 LE words).
-template <class F>
+template <class F, bool SYNC = false>
 HDN Jac<F> scalar_mul(const Aff<F>& p, const uint32_t* k) {
   Jac<F> acc = jac_identity<F>();
   bool started = false;
   for (int i = 255; i >= 0; i--) {
+    if (SYNC && (i & 3) == 3) BN_PHASE_SYNC();
     if (started) acc = jac_double(acc);
     if ((k[i >> 5] >> (i & 31)) & 1) {
       acc = jac_add_mixed(acc, p);
@@ -157,7 +158,7 @@ HDN bool g2_in_subgroup(const G2Aff& q) {
   // 6x^2 = 0x6f4d8248eeb859fbf83e9682e87cfd46 (127 bits).  Exactness: psi satisfies
   // psi^2 - t psi + p = 0 and gcd((6x^2)^2 - t 6x^2 + p, #E'(Fq2)/r) = 1, so the test forces ord(P) | r.
   const uint32_t k[8] = {0xe87cfd46u, 0xf83e9682u, 0xeeb859fbu, 0x6f4d8248u, 0, 0, 0, 0};
-  G2Jac lhs = scalar_mul(q, k);
+  G2Jac lhs = scalar_mul<Fp2, true>(q, k);
   G2Aff ps = g2_psi(q);
   // compare projective lhs with affine ps: X = x Z^2, Y = y Z^3
   if (is_identity(lhs)) return false;

@@ -23,6 +23,20 @@
 #define HDN static __attribute__((noinline))
 #endif
 
+// Phase barrier.  Every thread of a block runs the same data-independent sequence of big operations, but warps drift
+// apart and then each one pulls a different part of the (hundreds of KB of) pairing code through the SM's instruction
+// cache.  A block-wide barrier at the boundaries of the big operations keeps all warps of the block inside the same
+// function at the same time, so the instruction working set is one function, not the whole kernel.  Threads that
+// finished early (rejected / malformed proofs) have exited and do not take part in the barrier.
+// RULE: only code that every live thread of the block executes the same number of times may contain the barrier
+// (miller_loop, exp_by_neg_z, final_exponentiation, the subgroup check); generic helpers that callers may invoke
+// under a data-dependent branch (fe_pow_words, scalar_mul<false>, jac_*) must not.
+#if defined(__CUDA_ARCH__)
+#define BN_PHASE_SYNC() __syncthreads()
+#else
+#define BN_PHASE_SYNC()
+#endif
+
 namespace bn254 {
 
 // ---------------------------------------------------------------------------------------------

@@ -16,8 +16,15 @@ namespace bn254 {
 
 #define BN_MAX_IC 9  // up to 8 public inputs
 
+// Fixed-base tables for prepare_inputs: the IC bases are VK-constant, so [x] IC_i is a sum of 32 table entries
+// T[i][w][d-1] = d * 2^(8w) * IC_{i+1}, d = 1..255 (affine), one per non-zero byte of x.  Same group element as
+// the reference's 254-bit double-and-add, hence the same affine L.
+#define BN_IC_WINDOWS 32
+#define BN_IC_ENTRIES 255
+
 struct Groth16VkDev {
   int n_ic;
+  const G1Aff* ic_table;     // [n_ic - 1][BN_IC_WINDOWS][BN_IC_ENTRIES] in device memory, or null
   G1Aff alpha;
   G2Aff beta, gamma, delta;  // already sign-adjusted (beta', gamma', delta')
   G1Aff ic[BN_MAX_IC];
@@ -30,8 +37,23 @@ struct Groth16VkDev {
 HD void groth16_vk_prepare(Groth16VkDev& vk) {
   g2_precompute(vk.gamma_lines, vk.gamma);
   g2_precompute(vk.delta_lines, vk.delta);
-  Fp12 f = miller_loop<1, 0>(&vk.alpha, &vk.beta, nullptr, nullptr);
-  vk.target = final_exponentiation(f);
+  Fp12 f;
+  miller_loop<1, 0>(f, &vk.alpha, &vk.beta, nullptr, nullptr);
+  final_exponentiation(vk.target, f);
+}
+
+// One (base, window) slice of the fixed-base table.
+HD void groth16_ic_table_slice(G1Aff* out, const G1Aff& base, int w) {
+  G1Jac b = to_jac(base);
+  for (int i = 0; i < 8 * w; i++) b = jac_double(b);
+  G1Aff step;
+  to_affine(step, b);  // a VK point has order r: never the identity
+  G1Jac cur = b;
+  out[0] = step;
+  for (int d = 2; d <= BN_IC_ENTRIES; d++) {
+    cur = jac_add_mixed(cur, step);
+    to_affine(out[d - 1], cur);
+  }
 }
 
 // L = IC_0 + sum x_i IC_{i+1}; affine accumulation semantics of the reference: an identity term
@@ -42,7 +64,17 @@ HD int groth16_prepare_inputs(G1Aff& L, const Groth16VkDev& vk, const uint8_t* i
   for (int i = 0; i < n_inputs; i++) {
     Fr x;
     if (!fr_load_be_plain(x, inputs_be + 32 * i)) return BN254V_PANIC_FIELD_NOT_MEMBER;
-    G1Jac term = scalar_mul(vk.ic[i + 1], x.v);
+    G1Jac term;
+    if (vk.ic_table) {
+      term = jac_identity<Fp>();
+      const G1Aff* tab = vk.ic_table + (size_t)i * BN_IC_WINDOWS * BN_IC_ENTRIES;
+      for (int w = 0; w < BN_IC_WINDOWS; w++) {
+        uint32_t d = (x.v[w >> 2] >> (8 * (w & 3))) & 0xff;
+        if (d) term = jac_add_mixed(term, tab[w * BN_IC_ENTRIES + (d - 1)]);
+      }
+    } else {
+      term = scalar_mul(vk.ic[i + 1], x.v);
+    }
     if (is_identity(term)) return BN254V_PANIC_IDENTITY;
     acc = jac_add(acc, term);
     if (is_identity(acc)) return BN254V_PANIC_IDENTITY;
@@ -77,11 +109,12 @@ HD int groth16_verify_one(const Groth16VkDev& vk, const uint8_t* proof, uint32_t
 
   G1Aff pf[2] = {L, C};
   const Line* tabs[2] = {vk.gamma_lines, vk.delta_lines};
-  Fp12 f = miller_loop<1, 2>(&A, &B, pf, tabs);
+  Fp12 f;
+  miller_loop<1, 2>(f, &A, &B, pf, tabs);
   if (dbg.miller) fp12_to_bytes(dbg.miller, f);
-  Fp12 gt = final_exponentiation(f);
-  if (dbg.gt) fp12_to_bytes(dbg.gt, gt);
-  return eq(gt, vk.target) ? BN254V_OK_TRUE : BN254V_OK_FALSE;
+  final_exponentiation(f, f);
+  if (dbg.gt) fp12_to_bytes(dbg.gt, f);
+  return eq(f, vk.target) ? BN254V_OK_TRUE : BN254V_OK_FALSE;
 }
 
 // Raw k-pair product (bn::pairing_batch): all G2 variable.  A pair whose G1 bytes are all zero is
@@ -94,11 +127,12 @@ HD bool pairing_product_one(const uint8_t* g1, const uint8_t* g2, uint8_t* mille
     load_g1_unchecked(p[j], g1 + 64 * j);
     load_g2_unchecked(q[j], g2 + 128 * j);
   }
-  Fp12 f = miller_loop<KP, 0>(p, q, nullptr, nullptr);
+  Fp12 f;
+  miller_loop<KP, 0>(f, p, q, nullptr, nullptr);
   if (miller_out) fp12_to_bytes(miller_out, f);
-  Fp12 gt = final_exponentiation(f);
-  if (gt_out) fp12_to_bytes(gt_out, gt);
-  return eq(gt, fp12_one());
+  final_exponentiation(f, f);
+  if (gt_out) fp12_to_bytes(gt_out, f);
+  return eq(f, fp12_one());
 }
 
 }  // namespace bn254

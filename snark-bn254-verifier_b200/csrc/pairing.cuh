@@ -54,7 +54,7 @@ HD G2Aff g2_mul_by_q(const G2Aff& q) { return g2_psi(q); }
 
 // f <- f * line(P): mul_by_024(ell_0, ell_vw * P.y, ell_vv * P.x)
 HDN void apply_line(Fp12& f, const Line& l, const G1Aff& p) {
-  f = mul_by_024(f, l.ell_0, scale(l.ell_vw, p.y), scale(l.ell_vv, p.x));
+  mul_by_024(f, l.ell_0, scale(l.ell_vw, p.y), scale(l.ell_vv, p.x));
 }
 
 #define BN_N_LINES 87
@@ -80,8 +80,8 @@ HDN void g2_precompute(Line* out, const G2Aff& q) {
 // fly) and NF pairs whose G2 point has a precomputed line table.
 // `active_v` / `active_f`: pairs with an identity member are skipped (substrate-bn pairing_batch).
 template <int NV, int NF>
-HD Fp12 miller_loop(const G1Aff* pv, const G2Aff* qv, const G1Aff* pf, const Line* const* tables) {
-  Fp12 f = fp12_one();
+HD void miller_loop(Fp12& f, const G1Aff* pv, const G2Aff* qv, const G1Aff* pf, const Line* const* tables) {
+  f = fp12_one();
   G2Jac r[NV > 0 ? NV : 1];
   G2Aff nq[NV > 0 ? NV : 1];
   for (int v = 0; v < NV; v++) {
@@ -90,23 +90,31 @@ HD Fp12 miller_loop(const G1Aff* pv, const G2Aff* qv, const G1Aff* pf, const Lin
   }
   int idx = 0;
   for (int k = 0; k < 64; k++) {
-    f = sqr(f);
+    BN_PHASE_SYNC();
+    sqr(f, f);
     for (int v = 0; v < NV; v++) {
+      BN_PHASE_SYNC();
       Line l = doubling_step(r[v]);
+      BN_PHASE_SYNC();
       apply_line(f, l, pv[v]);
     }
+    BN_PHASE_SYNC();
     for (int t = 0; t < NF; t++) apply_line(f, tables[t][idx], pf[t]);
     idx++;
     int d = K::ate_digit(k);
     if (d != 0) {
       for (int v = 0; v < NV; v++) {
+        BN_PHASE_SYNC();
         Line l = addition_step(r[v], d == 1 ? qv[v] : nq[v]);
+        BN_PHASE_SYNC();
         apply_line(f, l, pv[v]);
       }
+      BN_PHASE_SYNC();
       for (int t = 0; t < NF; t++) apply_line(f, tables[t][idx], pf[t]);
       idx++;
     }
   }
+  BN_PHASE_SYNC();
   // Frobenius additions: all pairs consume coefficient idx (Q1) then idx+1 (Q2), as
   // substrate-bn's miller_loop_batch shares the coefficient index across pairs.
   G2Aff q1[NV > 0 ? NV : 1], q2[NV > 0 ? NV : 1];
@@ -125,45 +133,54 @@ HD Fp12 miller_loop(const G1Aff* pv, const G2Aff* qv, const G1Aff* pf, const Lin
     apply_line(f, l, pv[v]);
   }
   for (int t = 0; t < NF; t++) apply_line(f, tables[t][idx], pf[t]);
-  return f;
 }
 
-// conj(a^x), x = BN parameter, square-and-multiply with cyclotomic squarings
-HDN Fp12 exp_by_neg_z(const Fp12& a) {
-  Fp12 r = a;  // leading one of x (bit 62)
+// r = conj(a^x), x = BN parameter, square-and-multiply with cyclotomic squarings (r must not alias a)
+HDN void exp_by_neg_z(Fp12& r, const Fp12& a) {
+  r = a;  // leading one of x (bit 62)
   for (int i = 61; i >= 0; i--) {
-    r = cyclotomic_sqr(r);
-    if ((K::bn_x >> i) & 1) r = mul(r, a);
+    BN_PHASE_SYNC();
+    cyclotomic_sqr(r, r);
+    if ((K::bn_x >> i) & 1) {
+      BN_PHASE_SYNC();
+      mul(r, r, a);
+    }
   }
-  return conj(r);
+  BN_PHASE_SYNC();
+  conj(r, r);
 }
 
-// Fq12::final_exponentiation.  `f` must be non-zero (a Miller value always is).
-HDN Fp12 final_exponentiation(const Fp12& f) {
-  Fp12 t = mul(conj(f), inv(f));
-  t = mul(frobenius<2>(t), t);
-  Fp12 a = exp_by_neg_z(t);
-  Fp12 b = cyclotomic_sqr(a);
-  Fp12 c = cyclotomic_sqr(b);
-  Fp12 d = mul(c, b);
-  Fp12 e = exp_by_neg_z(d);
-  Fp12 ff = cyclotomic_sqr(e);
-  Fp12 g = exp_by_neg_z(ff);
-  Fp12 h = conj(d);
-  Fp12 i = conj(g);
-  Fp12 j = mul(i, e);
-  Fp12 k = mul(j, h);
-  Fp12 l = mul(k, b);
-  Fp12 m = mul(k, e);
-  Fp12 n = mul(t, m);
-  Fp12 o = frobenius<1>(l);
-  Fp12 p = mul(o, n);
-  Fp12 q = frobenius<2>(k);
-  Fp12 rr = mul(q, p);
-  Fp12 s = conj(t);
-  Fp12 t2 = mul(s, l);
-  Fp12 u = frobenius<3>(t2);
-  return mul(u, rr);
+// Fq12::final_exponentiation (r may alias f).  `f` must be non-zero (a Miller value always is).
+// Same chain as substrate-bn, written over 8 reused buffers.
+HDN void final_exponentiation(Fp12& r, const Fp12& f) {
+  Fp12 T, A, B, D, E, Kk, L, X;
+  inv(A, f);
+  conj(X, f);
+  mul(T, X, A);  // f^(p^6 - 1)
+  frobenius<2>(A, T);
+  mul(T, A, T);  // t = f^((p^6-1)(p^2+1))
+  exp_by_neg_z(A, T);      // a
+  cyclotomic_sqr(B, A);    // b
+  cyclotomic_sqr(X, B);    // c
+  mul(D, X, B);            // d
+  exp_by_neg_z(E, D);      // e
+  cyclotomic_sqr(X, E);    // f
+  exp_by_neg_z(A, X);      // g
+  conj(A, A);              // i = conj(g)
+  mul(Kk, A, E);           // j = i e
+  conj(X, D);              // h
+  mul(Kk, Kk, X);          // k = j h
+  mul(L, Kk, B);           // l = k b
+  mul(X, Kk, E);           // m = k e
+  mul(X, T, X);            // n = t m
+  frobenius<1>(A, L);      // o
+  mul(X, A, X);            // p = o n
+  frobenius<2>(A, Kk);     // q
+  mul(X, A, X);            // r = q p
+  conj(A, T);              // s
+  mul(A, A, L);            // t' = s l
+  frobenius<3>(B, A);      // u
+  mul(r, B, X);
 }
 
 }  // namespace bn254

@@ -373,11 +373,12 @@ HD int plonk_verify_one(const PlonkVkDev& vk, const uint8_t* pr, uint32_t len, c
     store_g1(dbg.g1 + 192, pf[1]);
   }
   const Line* tabs[2] = {vk.g2_lines[0], vk.g2_lines[1]};
-  Fp12 f = miller_loop<0, 2>(nullptr, nullptr, pf, tabs);
+  Fp12 f;
+  miller_loop<0, 2>(f, nullptr, nullptr, pf, tabs);
   if (dbg.miller) fp12_to_bytes(dbg.miller, f);
-  Fp12 gt = final_exponentiation(f);
-  if (dbg.gt) fp12_to_bytes(dbg.gt, gt);
-  return eq(gt, fp12_one()) ? BN254V_OK_TRUE : BN254V_ERR_PAIRING_CHECK_FAILED;
+  final_exponentiation(f, f);
+  if (dbg.gt) fp12_to_bytes(dbg.gt, f);
+  return eq(f, fp12_one()) ? BN254V_OK_TRUE : BN254V_ERR_PAIRING_CHECK_FAILED;
 }
 
 }  // namespace bn254

@@ -53,9 +53,23 @@ void* hs_groth16_vk_new(const uint8_t* vk_points, int n_ic) {
   load_g2_unchecked(vk->delta, vk_points + 320);
   for (int i = 0; i < n_ic; i++) load_g1_unchecked(vk->ic[i], vk_points + 448 + 64 * i);
   groth16_vk_prepare(*vk);
+  vk->ic_table = nullptr;
   return vk;
 }
-void hs_groth16_vk_free(void* vk) { delete (Groth16VkDev*)vk; }
+// same, with the fixed-base IC tables the CUDA vk_load builds
+void* hs_groth16_vk_new_tables(const uint8_t* vk_points, int n_ic) {
+  Groth16VkDev* vk = (Groth16VkDev*)hs_groth16_vk_new(vk_points, n_ic);
+  G1Aff* tab = new G1Aff[(size_t)(n_ic - 1) * BN_IC_WINDOWS * BN_IC_ENTRIES];
+  for (int b = 0; b + 1 < n_ic; b++)
+    for (int w = 0; w < BN_IC_WINDOWS; w++)
+      groth16_ic_table_slice(tab + ((size_t)b * BN_IC_WINDOWS + w) * BN_IC_ENTRIES, vk->ic[b + 1], w);
+  vk->ic_table = tab;
+  return vk;
+}
+void hs_groth16_vk_free(void* vk) {
+  delete[] ((Groth16VkDev*)vk)->ic_table;
+  delete (Groth16VkDev*)vk;
+}
 void hs_groth16_vk_target(void* vk, uint8_t* out) { fp12_to_bytes(out, ((Groth16VkDev*)vk)->target); }
 
 int hs_groth16_verify(void* vk, const uint8_t* proof, uint32_t proof_len, const uint8_t* inputs, int n_inputs,

@@ -64,9 +64,11 @@ def test_groth16_matches_golden(hs):
                                      ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]
     hs.hs_groth16_vk_target.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
     hs.hs_groth16_vk_free.argtypes = [ctypes.c_void_p]
-    for case in load_json("groth16_golden.json")["cases"]:
+    hs.hs_groth16_vk_new_tables.restype = ctypes.c_void_p
+    for ci, case in enumerate(load_json("groth16_golden.json")["cases"]):
         blob, n_ic = _vk_points(case)
-        vk = hs.hs_groth16_vk_new(blob, n_ic)
+        # case 0: prepare_inputs through the fixed-base tables (what the CUDA vk_load builds); case 1: double-and-add
+        vk = (hs.hs_groth16_vk_new_tables if ci == 0 else hs.hs_groth16_vk_new)(blob, n_ic)
         tgt = ctypes.create_string_buffer(384)
         hs.hs_groth16_vk_target(vk, tgt)
         assert tgt.raw.hex() == case["alpha_beta"]
@@ -86,7 +88,8 @@ def test_groth16_malformed_classes(hs, pkg):
     hs.hs_groth16_vk_new.restype = ctypes.c_void_p
     hs.hs_groth16_verify.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_int,
                                      ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]
-    vk = hs.hs_groth16_vk_new(blob, n_ic)
+    hs.hs_groth16_vk_new_tables.restype = ctypes.c_void_p
+    vk = hs.hs_groth16_vk_new_tables(blob, n_ic)
     names = {"OK_TRUE": 0, "OK_FALSE": 1, "ERR_PREPARE_INPUTS": 2, "PANIC_FIELD_NOT_MEMBER": 16, "PANIC_NOT_ON_CURVE": 17,
              "PANIC_NOT_IN_SUBGROUP": 18, "PANIC_IDENTITY": 19, "PANIC_SHORT_BUFFER": 20}
     for name, pb, xs, want in groth16_malformed_suite(td):

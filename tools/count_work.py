@@ -20,7 +20,7 @@ def main(write=True):
     from helpers import build_hostsim, load_json, plonk_fixture, plonk_vk_bytes
     hs = build_hostsim()
     hs.hs_mul_count.restype = ctypes.c_ulonglong
-    hs.hs_groth16_vk_new.restype = ctypes.c_void_p
+    hs.hs_groth16_vk_new_tables.restype = ctypes.c_void_p
     hs.hs_groth16_verify.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_int,
                                      ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]
     hs.hs_plonk_vk_new.restype = ctypes.c_void_p
@@ -34,7 +34,7 @@ def main(write=True):
     vk = bo.load_groth16_verifying_key_from_bytes(bytes.fromhex(case["vk"]))
     blob = bo.g1_to_bytes(vk["alpha"]) + bo.g2_to_bytes(vk["beta2"]) + bo.g2_to_bytes(vk["gamma2"]) + \
         bo.g2_to_bytes(bo.g2_neg(vk["delta2"])) + b"".join(bo.g1_to_bytes(k) for k in vk["k"])
-    h = hs.hs_groth16_vk_new(blob, len(vk["k"]))
+    h = hs.hs_groth16_vk_new_tables(blob, len(vk["k"]))
     hs.hs_mul_count(1)
     n = 0
     for pr in case["proofs"]:
