@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="proofs in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the PlonK / raw pairing-product side measurements")
     return ap.parse_args()
 
 
@@ -127,7 +128,7 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ref_cpu
     cores = host_cores()
-    sample = args.cpu_sample or max(cores * 24, 256)
+    sample = args.cpu_sample or max(cores * 256, 512)
     vk, proofs, inputs, expected = ref_cpu.groth16_synth(SEED, sample)
     times = []
     for it in range(args.warmup + args.steps):
@@ -141,7 +142,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "groth16 trapdoor-simulated proofs, 2 public inputs, 50% corrupted "
+        "config": {"workload": "groth16 trapdoor-simulated proofs, 2 public inputs, 50%% corrupted "
                                "(BASELINE.json configs[1]); bounded sample of %d proofs per step" % sample,
                    "seed": SEED},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
@@ -152,6 +153,46 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def secondary_workloads(pkg, work):
+    """Side measurements on rank 0 (end to end through the C ABI from host buffers, wall clock around the synchronous
+    call): BASELINE.json configs[2] (2^14 PlonK proofs from the bundled fixtures, 50 % mutated) and configs[3] scaled
+    to 2^17 raw 4-pair products.  Reported next to the headline; the headline metric stays Groth16 configs[1]."""
+    import numpy as np
+    import workloads
+    out = {}
+    n = 1 << 14
+    proofs, inputs, rnd, expected = workloads.plonk_workload(n, seed=3)
+    vk = workloads.plonk_vk_bytes()
+    pkg.PlonkVerifier.verify_batch(proofs[:512], vk, inputs[:512], rnd=rnd[:512])  # VK load + warm-up
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        st = pkg.PlonkVerifier.verify_batch(proofs, vk, inputs, rnd=rnd)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    assert (st == expected).all(), "PlonK status mismatch"
+    out["plonk"] = {"workload": "2^14 PlonK proofs = 4 bundled SP1 fixtures replicated, 50% mutated (BASELINE configs[2])",
+                    "e2e_proofs_per_sec": n / best, "ms": best * 1e3,
+                    "field_mults_full_path": work.get("plonk_full_path_mul"),
+                    "note": "mutated proofs split between early reject (OpeningPolyMismatch) and full-path reject"}
+    p2, i2, r2, e2 = workloads.plonk_workload(n, seed=4, late_reject_only=True)
+    t0 = time.perf_counter()
+    st = pkg.PlonkVerifier.verify_batch(p2, vk, i2, rnd=r2)
+    dt = time.perf_counter() - t0
+    assert (st == e2).all()
+    out["plonk"]["late_reject_only_proofs_per_sec"] = n / dt
+    m = 1 << 17
+    g1, g2, exp1 = pkg.pairing_synth(11, m, k=4)
+    pkg.pairing_product_batch(g1[:1024], g2[:1024], 4)
+    t0 = time.perf_counter()
+    one = pkg.pairing_product_batch(g1, g2, 4)
+    dt = time.perf_counter() - t0
+    assert (one == exp1).all()
+    out["pairing_product_k4"] = {"workload": "2^17 random 4-pair sets, all G2 variable (BASELINE configs[3] scaled)",
+                                 "e2e_sets_per_sec": m / dt, "pair_miller_loops_per_sec": 4 * m / dt, "ms": dt * 1e3}
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -256,9 +297,9 @@ def run_b200(args):
         "bound": "int32-imad", "achieved": achieved / 1e12, "peak": peak["wide_mac_per_s"] / 1e12, "unit": "TMAC/s",
         "frac": achieved / peak["wide_mac_per_s"], "traffic": None,
         "kernel": "k_groth16_verify", "macs_per_proof": macs_per_proof, "fp_mul_per_proof": work["groth16_fp_mul"],
-        "peak_source": "measured live: bn254v_imad_peak (dependent-free IMAD.WIDE.U32 stream, all SMs); "
-                       "MEASURED_PEAKS.json holds no integer peak",
-        "peak_lo_imad_tmacs": peak["lo_mac_per_s"] / 1e12,
+        "peak_source": "measured live: bn254v_imad_peak (independent IMAD.WIDE.U32 accumulate chains, 8 warps/SMSP, "
+                       "all SMs); MEASURED_PEAKS.json holds no integer peak",
+        "peak_imad32_tmacs": peak["lo_mac_per_s"] / 1e12,
         "hbm_gbs_algorithmic": (h2d + d2h) * args.steps / (sum(kernel_ms) * 1e-3) / 1e9,
         "note": "tensor cores unused: carry-chained multiprecision integer arithmetic; HBM traffic negligible",
     }
@@ -267,7 +308,7 @@ def run_b200(args):
     if not args.no_cpu_baseline:
         try:
             cores = host_cores()
-            sample = args.cpu_sample or max(cores * 24, 256)
+            sample = args.cpu_sample or max(cores * 512, 512)
             sample = min(sample, n)
             dt, st_cpu = cpu_reference_run(vk, proofs[:sample], inputs[:sample], cores)
             assert (st_cpu == expected[:sample]).all(), "CPU oracle disagrees with expected verdicts"
@@ -275,6 +316,10 @@ def run_b200(args):
                    "sample": "first %d proofs of the same batch, one pass, %.1f s" % (sample, dt)}
         except Exception as e:  # the baseline is a reported number, never a dependency of the product path
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "unavailable: %r" % (e,)}
+
+    extra = {}
+    if not args.no_secondary:
+        extra = secondary_workloads(pkg, work)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -289,6 +334,7 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "pairings_per_sec": 3 * value,
         "wall_s_kernel_loop": wall_kernel,
+        **extra,
     }
     print(json.dumps(line))
     if dist is not None:

@@ -129,7 +129,8 @@ __global__ void k_plonk_vk_prepare(PlonkVkDev* vk) {
   if (blockIdx.x == 0 && threadIdx.x == 0) plonk_vk_prepare(*vk);
 }
 
-__global__ void __launch_bounds__(BN_TPB)
+template <int TPB>
+__global__ void __launch_bounds__(TPB, 1)
     k_plonk_verify(const PlonkVkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride,
                    const uint32_t* __restrict__ proof_len, const uint8_t* __restrict__ inputs, int n_inputs,
                    const uint8_t* __restrict__ rnd, size_t n, uint8_t* __restrict__ status, uint8_t* dbg_g1,
@@ -144,8 +145,8 @@ __global__ void __launch_bounds__(BN_TPB)
                                         rnd + 32 * i, dbg);
 }
 
-template <int KP>
-__global__ void __launch_bounds__(BN_TPB)
+template <int KP, int TPB>
+__global__ void __launch_bounds__(TPB, 1)
     k_pairing_product(const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2, size_t n,
                       uint8_t* __restrict__ is_one, uint8_t* miller_out, uint8_t* gt_out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -173,49 +174,56 @@ __global__ void __launch_bounds__(BN_TPB)
   pairing_synth_one(g1 + (size_t)64 * k * i, g2 + (size_t)128 * k * i, expected + i, seed, first + i, k);
 }
 
-// Launch-shape variants (threads per block x resident blocks per SM -> registers per thread); the default is
-// the one measured fastest on B200 (profiles/), BN254V_VARIANT overrides it for experiments.
+// Launch shapes.  One proof per thread; the block is the unit that the phase barriers keep in step, and the grid should
+// cover the SMs evenly.  `pick_shape`: big batches use 448-thread blocks, one per SM (14 warps, 128 registers/thread;
+// 2^16 proofs = 147 blocks on 148 SMs); small batches use smaller blocks so that every SM gets work.
+// BN254V_VARIANT overrides the choice for experiments (1: 128x2, 2: 128x4, 3: 448x1, 4: 512x1, 5: 256x2, 6: 32x1).
+static int g_sm_count = 148;
+static int pick_shape(size_t m) {
+  static int forced = -2;
+  if (forced == -2) {
+    const char* e = getenv("BN254V_VARIANT");
+    forced = e ? atoi(e) : -1;
+  }
+  if (forced >= 1) return forced;
+  if (m >= (size_t)g_sm_count * 448 * 3 / 4) return 3;  // 448 x 1
+  if (m >= (size_t)g_sm_count * 128) return 1;          // 128 x 2
+  return 6;                                             // 32-thread blocks: spread thin batches over all SMs
+}
+
 static void launch_groth16_verify(cudaStream_t st, const Groth16VkDev* vk, const uint8_t* proofs, size_t stride,
                                   const uint32_t* lens, const uint8_t* inputs, int n_inputs, size_t m, uint8_t* status,
                                   uint8_t* l, uint8_t* ml, uint8_t* gt) {
-  static int variant = -1;
-  if (variant < 0) {
-    const char* e = getenv("BN254V_VARIANT");
-    variant = e ? atoi(e) : 0;
-  }
 #define LV(TPB, MINB)                                                                                              \
   k_groth16_verify<TPB, MINB><<<(unsigned)((m + TPB - 1) / TPB), TPB, 0, st>>>(vk, proofs, stride, lens, inputs, \
                                                                                n_inputs, m, status, l, ml, gt)
-  switch (variant) {
-    case 1: LV(128, 3); break;
+  switch (pick_shape(m)) {
     case 2: LV(128, 4); break;
-    case 3: LV(64, 4); break;
-    case 4: LV(64, 6); break;
-    case 5: LV(64, 8); break;
-    case 6: LV(32, 8); break;
-    case 7: LV(448, 1); break;
-    case 8: LV(512, 1); break;
-    case 9: LV(256, 2); break;
-    case 10: LV(256, 1); break;
-    case 11: LV(384, 1); break;
+    case 3: LV(448, 1); break;
+    case 4: LV(512, 1); break;
+    case 5: LV(256, 2); break;
+    case 6: LV(32, 1); break;
     default: LV(128, 2); break;
   }
 #undef LV
 }
 
-// Integer multiply-add issue-rate probe: 8 independent chains per thread, 8 warps per SMSP.  Each step is one
-// IMAD.WIDE.U32 with a 64-bit accumulate (written as the mad.lo.cc / madc.hi pair ptxas fuses, exactly as in fe_mul)
-// or one 32-bit IMAD, plus one LOP3 on the ALU pipe that refreshes the multiplicand so that ptxas can neither hoist
-// nor strength-reduce the products (SASS checked: 32 IMAD.WIDE.U32 / IMAD + 32 LOP3 per unrolled iteration).
+// Integer multiply-add issue-rate probe (the roofline denominator): 8 independent accumulator chains per thread,
+// 8 warps per SMSP.  Each step is one IMAD.WIDE.U32 with a 64-bit accumulate -- written as the mad.lo.cc / madc.hi
+// pair that ptxas fuses, exactly as in fe_mul -- or one 32-bit IMAD.  The multiplier a[u] changes every iteration
+// (one IADD per 8 MACs) so that ptxas can neither hoist the products nor strength-reduce the loop; SASS checked:
+// 32 IMAD.WIDE.U32 (or IMAD) + 4 IADD3 per unrolled iteration.  Measured on B200 at 1965 MHz: 8.69 T wide MAC/s
+// (one warp-wide IMAD.WIDE per 4.3 cycles per SMSP) and 18.5 T 32-bit IMAD/s (one per 2.0 cycles).
 template <bool WIDE>
 __global__ void __launch_bounds__(256) k_imad_peak(int iters, uint32_t a0, uint32_t b0, uint64_t* sink) {
-  uint32_t a = a0 + threadIdx.x;
-  uint32_t lo[8], hi[8], x[8];
+  uint32_t lo[8], hi[8], x[8], a[4];
+#pragma unroll
+  for (int u = 0; u < 4; u++) a[u] = a0 * (u + 1) + threadIdx.x;
 #pragma unroll
   for (int j = 0; j < 8; j++) {
     lo[j] = blockIdx.x;
     hi[j] = b0 + j;
-    x[j] = j + a;
+    x[j] = (j + 1) * b0 + threadIdx.x;
   }
   for (int it = 0; it < iters; it++) {
 #pragma unroll
@@ -225,11 +233,11 @@ __global__ void __launch_bounds__(256) k_imad_peak(int iters, uint32_t a0, uint3
         if (WIDE)
           asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;"
                        : "+r"(lo[j]), "+r"(hi[j])
-                       : "r"(x[j]), "r"(a));
+                       : "r"(x[j]), "r"(a[u]));
         else
-          asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[j]) : "r"(x[j]), "r"(a));
-        x[j] ^= lo[j];
+          asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[j]) : "r"(x[j]), "r"(a[u]));
       }
+      a[u] += 0x9e3779b9u;
     }
   }
   uint32_t s = 0;
@@ -263,6 +271,7 @@ int bn254v_init(const int* devices, int n_devices) {
     Dev d;
     d.id = id;
     CU(cudaSetDevice(id));
+    CU(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, id));
     CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&d.ev0));
     CU(cudaEventCreate(&d.ev1));
@@ -542,12 +551,17 @@ int bn254v_plonk_verify_batch(const bn254v_vk* vk, const uint8_t* proofs, size_t
     if (p.fr.p) CU(cudaMemsetAsync(p.fr.p, 0, m * 256, dev.stream));
     if (p.m.p) CU(cudaMemsetAsync(p.m.p, 0, m * 384, dev.stream));
     if (p.gt.p) CU(cudaMemsetAsync(p.gt.p, 0, m * 384, dev.stream));
-    unsigned grid = (unsigned)((m + BN_TPB - 1) / BN_TPB);
-    k_plonk_verify<<<grid, BN_TPB, 0, dev.stream>>>((const PlonkVkDev*)vk->dev[d], p.proofs.as<uint8_t>(), proof_stride,
-                                                    proof_len ? p.lens.as<uint32_t>() : nullptr, p.inputs.as<uint8_t>(),
-                                                    n_inputs, p.rnd.as<uint8_t>(), m, p.status.as<uint8_t>(),
-                                                    p.g1.as<uint8_t>(), p.fr.as<uint8_t>(), p.m.as<uint8_t>(),
-                                                    p.gt.as<uint8_t>());
+#define LAUNCH_PK(TPB)                                                                                            \
+  k_plonk_verify<TPB><<<(unsigned)((m + TPB - 1) / TPB), TPB, 0, dev.stream>>>(                                  \
+      (const PlonkVkDev*)vk->dev[d], p.proofs.as<uint8_t>(), proof_stride, proof_len ? p.lens.as<uint32_t>() : nullptr, \
+      p.inputs.as<uint8_t>(), n_inputs, p.rnd.as<uint8_t>(), m, p.status.as<uint8_t>(), p.g1.as<uint8_t>(),        \
+      p.fr.as<uint8_t>(), p.m.as<uint8_t>(), p.gt.as<uint8_t>())
+    switch (pick_shape(m)) {
+      case 3: case 4: LAUNCH_PK(448); break;
+      case 6: LAUNCH_PK(32); break;
+      default: LAUNCH_PK(128); break;
+    }
+#undef LAUNCH_PK
     g_launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(status + lo, p.status.p, m, cudaMemcpyDeviceToHost, dev.stream));
@@ -590,10 +604,15 @@ int bn254v_pairing_product_batch(const uint8_t* g1, const uint8_t* g2, int k, si
     if (gt_out) CU(p.gt.alloc(m * 384));
     CU(cudaMemcpyAsync(p.g1.p, g1 + lo * 64 * k, m * 64 * k, cudaMemcpyHostToDevice, dev.stream));
     CU(cudaMemcpyAsync(p.g2.p, g2 + lo * 128 * k, m * 128 * k, cudaMemcpyHostToDevice, dev.stream));
-    unsigned grid = (unsigned)((m + BN_TPB - 1) / BN_TPB);
-#define LAUNCH_PP(KP)                                                                                   \
-  k_pairing_product<KP><<<grid, BN_TPB, 0, dev.stream>>>(p.g1.as<uint8_t>(), p.g2.as<uint8_t>(), m,    \
-                                                         p.one.as<uint8_t>(), p.m.as<uint8_t>(), p.gt.as<uint8_t>())
+#define LAUNCH_PP2(KP, TPB)                                                                             \
+  k_pairing_product<KP, TPB><<<(unsigned)((m + TPB - 1) / TPB), TPB, 0, dev.stream>>>(                 \
+      p.g1.as<uint8_t>(), p.g2.as<uint8_t>(), m, p.one.as<uint8_t>(), p.m.as<uint8_t>(), p.gt.as<uint8_t>())
+#define LAUNCH_PP(KP)                          \
+  switch (pick_shape(m)) {                     \
+    case 3: case 4: LAUNCH_PP2(KP, 448); break; \
+    case 6: LAUNCH_PP2(KP, 32); break;         \
+    default: LAUNCH_PP2(KP, 128); break;       \
+  }
     switch (k) {
       case 1: LAUNCH_PP(1); break;
       case 2: LAUNCH_PP(2); break;
@@ -601,6 +620,7 @@ int bn254v_pairing_product_batch(const uint8_t* g1, const uint8_t* g2, int k, si
       default: LAUNCH_PP(4); break;
     }
 #undef LAUNCH_PP
+#undef LAUNCH_PP2
     g_launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(is_one + lo, p.one.p, m, cudaMemcpyDeviceToHost, dev.stream));

@@ -154,16 +154,43 @@ HD G2Aff g2_psi(const G2Aff& q) {
   BN_LOAD_FP2(cy, K::frob1, 2);  // xi^((p-1)/2)
   return G2Aff{mul(conj(q.x), cx), mul(conj(q.y), cy)};
 }
-HDN bool g2_in_subgroup(const G2Aff& q) {
+// Reference predicate, 127-bit scalar: psi(P) == [6x^2]P (kept for cross-checking the faster test below).
+HDN bool g2_in_subgroup_6x2(const G2Aff& q) {
   // 6x^2 = 0x6f4d8248eeb859fbf83e9682e87cfd46 (127 bits).  Exactness: psi satisfies
   // psi^2 - t psi + p = 0 and gcd((6x^2)^2 - t 6x^2 + p, #E'(Fq2)/r) = 1, so the test forces ord(P) | r.
   const uint32_t k[8] = {0xe87cfd46u, 0xf83e9682u, 0xeeb859fbu, 0x6f4d8248u, 0, 0, 0, 0};
-  G2Jac lhs = scalar_mul<Fp2, true>(q, k);
+  G2Jac lhs = scalar_mul<Fp2, false>(q, k);
   G2Aff ps = g2_psi(q);
-  // compare projective lhs with affine ps: X = x Z^2, Y = y Z^3
   if (is_identity(lhs)) return false;
   Fp2 z2 = sqr(lhs.z);
   return eq(lhs.x, mul(ps.x, z2)) && eq(lhs.y, mul(ps.y, mul(z2, lhs.z)));
+}
+
+HD G2Jac g2_psi_jac(const G2Jac& p) {  // psi in Jacobian coordinates: conjugation commutes with X/Z^2, Y/Z^3
+  Fp2 cx, cy;
+  BN_LOAD_FP2(cx, K::frob1, 1);
+  BN_LOAD_FP2(cy, K::frob1, 2);
+  return G2Jac{mul(conj(p.x), cx), mul(conj(p.y), cy), conj(p.z)};
+}
+template <class F>
+HD bool jac_eq(const Jac<F>& a, const Jac<F>& b) {
+  bool ia = is_identity(a), ib = is_identity(b);
+  if (ia || ib) return ia && ib;
+  F za2 = sqr(a.z), zb2 = sqr(b.z);
+  return eq(mul(a.x, zb2), mul(b.x, za2)) && eq(mul(a.y, mul(zb2, b.z)), mul(b.y, mul(za2, a.z)));
+}
+// BN subgroup test with a 63-bit scalar (El Housni-Guillevic-Piellard, "Co-factor clearing and subgroup membership
+// testing on pairing-friendly curves", the test gnark-crypto uses for BN254):
+//   P in G2  <=>  [x+1]P + psi([x]P) + psi^2([x]P) == psi^3([2x]P).
+// Same predicate as substrate-bn's [r]P == 0 on every point of E'(Fq2), at a quarter of the doublings.
+HDN bool g2_in_subgroup(const G2Aff& q) {
+  const uint32_t k[8] = {0x4a6909f1u, 0x44e992b4u, 0, 0, 0, 0, 0, 0};  // x = 0x44e992b44a6909f1
+  G2Jac a = scalar_mul<Fp2, true>(q, k);  // [x]P
+  G2Jac b = g2_psi_jac(a);                 // psi([x]P)
+  G2Jac c = g2_psi_jac(b);                 // psi^2([x]P)
+  G2Jac d = g2_psi_jac(c);                 // psi^3([x]P)
+  G2Jac lhs = jac_add(jac_add(jac_add_mixed(a, q), b), c);
+  return jac_eq(lhs, jac_double(d));
 }
 
 }  // namespace bn254

@@ -171,6 +171,18 @@ HD Fe<C> fe_add(const Fe<C>& a, const Fe<C>& b) {
   return r;
 }
 
+// a + b without the conditional subtraction: result < 2m < 2^255.  Only valid as a multiplier operand:
+// fe_mul(x, y) is fully reduced whenever x * y < 2^256 * m, which holds for x, y < 2m because 4m < 2^256.
+template <class C>
+HD Fe<C> fe_add_nr(const Fe<C>& a, const Fe<C>& b) {
+  Fe<C> r;
+  r.v[0] = cc::add_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) r.v[i] = cc::addc_cc(a.v[i], b.v[i]);
+  r.v[7] = cc::addc(a.v[7], b.v[7]);
+  return r;
+}
+
 template <class C>
 HD Fe<C> fe_sub(const Fe<C>& a, const Fe<C>& b) {
   Fe<C> r;

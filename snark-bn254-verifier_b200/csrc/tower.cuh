@@ -55,14 +55,14 @@ HD bool eq(const Fp2& a, const Fp2& b) { return fe_eq(a.c0, b.c0) && fe_eq(a.c1,
 HDN Fp2 mul(Fp2 a, Fp2 b) {
   Fp t0 = fe_mul(a.c0, b.c0);
   Fp t1 = fe_mul(a.c1, b.c1);
-  Fp s = fe_mul(fe_add(a.c0, a.c1), fe_add(b.c0, b.c1));
+  Fp s = fe_mul(fe_add_nr(a.c0, a.c1), fe_add_nr(b.c0, b.c1));  // operands < 2p: still fully reduced
   return Fp2{fe_sub(t0, t1), fe_sub(fe_sub(s, t0), t1)};
 }
 // (a0+a1)(a0-a1), 2 a0 a1
 HDN Fp2 sqr(Fp2 a) {
-  Fp t = fe_mul(a.c0, a.c1);
-  Fp c0 = fe_mul(fe_add(a.c0, a.c1), fe_sub(a.c0, a.c1));
-  return Fp2{c0, fe_dbl(t)};
+  Fp c1 = fe_mul(fe_add_nr(a.c0, a.c0), a.c1);  // 2 a0 a1 (first operand < 2p)
+  Fp c0 = fe_mul(fe_add_nr(a.c0, a.c1), fe_sub(a.c0, a.c1));
+  return Fp2{c0, c1};
 }
 HD Fp2 scale(const Fp2& a, const Fp& k) { return Fp2{fe_mul(a.c0, k), fe_mul(a.c1, k)}; }
 // multiply by xi = 9 + u: (9 a0 - a1) + (a0 + 9 a1) u

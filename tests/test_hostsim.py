@@ -159,3 +159,22 @@ def test_plonk_mutations_and_structural_cases(hs):
         st = hs.hs_plonk_verify(vk, pr, len(pr), inputs, len(xs), rnd, None, None, None, None)
         assert st == PLONK_STATUS[want], (name, want, st)
     hs.hs_plonk_vk_free(vk)
+
+
+def test_g2_subgroup_tests_agree(hs):
+    """The 63-bit subgroup test and the 127-bit one agree with the oracle's [r]P == 0 on subgroup points, on random
+    points of E'(Fq2) outside the subgroup, and on points of the form (subgroup point + cofactor-torsion point)."""
+    from helpers import g2_point_outside_subgroup
+    for k in (1, 2, 12345, bo.R - 1):
+        pt = bo.g2_mul(bo.G2_GEN, k)
+        assert hs.hs_g2_subgroup_both(bo.g2_to_bytes(pt)) == 3
+    for seed in (5, 6, 7, 100, 1000):
+        pt = g2_point_outside_subgroup(seed)
+        assert not bo.g2_in_subgroup(pt)
+        assert hs.hs_g2_subgroup_both(bo.g2_to_bytes(pt)) == 0
+        mixed = bo.g2_add(pt, bo.g2_mul(bo.G2_GEN, seed))
+        assert hs.hs_g2_subgroup_both(bo.g2_to_bytes(mixed)) == 0
+        # [r]P of an outside point is a non-trivial point killed by the cofactor: still outside
+        tors = bo.g2_mul_raw(pt, bo.R)
+        if tors is not None:
+            assert hs.hs_g2_subgroup_both(bo.g2_to_bytes(tors)) == 0
