@@ -214,6 +214,8 @@ def run_b200(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pkg = ge.load_package()
+    from importlib import import_module
+    sharding = import_module("snark_bn254_verifier_b200.sharding")
     pkg.init([local_rank])
     n = args.batch
 
@@ -276,10 +278,8 @@ def run_b200(args):
     t0 = time.perf_counter()
     for _ in range(args.steps):
         st = pkg.Groth16Verifier.verify_batch(np_proofs, vk, np_inputs)  # H2D + kernel + D2H, synchronous
-        if dist is not None:  # final gather of verdict bits (n/8 bytes per rank)
-            bits = torch.from_numpy(np.packbits(st == pkg.OK_TRUE)).cuda()
-            out = torch.empty(world * bits.numel(), dtype=torch.uint8, device="cuda")
-            dist.all_gather_into_tensor(out, bits)
+        if dist is not None:  # final gather of verdict bits (n/8 bytes per rank) -- the path's only exchange
+            verdicts = sharding.gather_verdicts(st, world * n, dist, device="cuda")
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     assert (st == expected).all()

@@ -58,12 +58,63 @@ int ensure_init() {
   return bn254v_init(nullptr, 0);
 }
 
-struct DevBuf {  // RAII device allocation on the current device
+// Scratch device memory is kept in a small per-device free list between calls: cudaMalloc / cudaFree cost
+// milliseconds (and cudaFree synchronises the device), which is visible next to a 50 ms batch.
+struct Block {
+  void* p;
+  size_t cap;
+  int dev;
+};
+std::vector<Block> g_pool;  // guarded by g_pool_mu
+std::mutex g_pool_mu;
+
+struct DevBuf {  // RAII scratch allocation on the current device (returned to the pool, not freed)
   void* p = nullptr;
+  size_t cap = 0;
+  int dev = -1;
   ~DevBuf() {
-    if (p) cudaFree(p);
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_pool.push_back(Block{p, cap, dev});
   }
-  cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+  cudaError_t alloc(size_t n) {
+    if (!n) n = 1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    {
+      std::lock_guard<std::mutex> lk(g_pool_mu);
+      int best = -1;
+      for (int i = 0; i < (int)g_pool.size(); i++)
+        if (g_pool[i].dev == dev && g_pool[i].cap >= n && g_pool[i].cap <= 2 * n + 4096 &&
+            (best < 0 || g_pool[i].cap < g_pool[best].cap))
+          best = i;
+      if (best >= 0) {
+        p = g_pool[best].p;
+        cap = g_pool[best].cap;
+        g_pool.erase(g_pool.begin() + best);
+        return cudaSuccess;
+      }
+    }
+    cap = n;
+    e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) {  // pool may be holding the memory: release it and retry once
+      pool_release(dev);
+      e = cudaMalloc(&p, n);
+    }
+    if (e != cudaSuccess) p = nullptr;
+    return e;
+  }
+  static void pool_release(int device) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (size_t i = 0; i < g_pool.size();) {
+      if (device < 0 || g_pool[i].dev == device) {
+        cudaFree(g_pool[i].p);
+        g_pool.erase(g_pool.begin() + i);
+      } else {
+        i++;
+      }
+    }
+  }
   template <class T>
   T* as() { return (T*)p; }
 };
@@ -79,6 +130,7 @@ inline void shard(size_t n, int d, int nd, size_t& lo, size_t& hi) {
 struct bn254v_vk {
   int kind;  // 0 groth16, 1 plonk
   int n_public;
+  int n_qcp = 0;  // PlonK: number of BSB22 commitments
   int sign_mode;
   std::vector<void*> dev;  // per device slot: Groth16VkDev* / PlonkVkDev*
   std::vector<void*> aux;  // per device slot: fixed-base tables (Groth16) or null
@@ -118,31 +170,80 @@ __global__ void __launch_bounds__(TPB, MINB)
                                           n_inputs, dbg);
 }
 
-// one thread per (IC base, window): builds the fixed-base table slices in parallel (once per VK)
-__global__ void k_groth16_ic_tables(const Groth16VkDev* vk, G1Aff* table) {
+// one thread per (base, window): builds the fixed-base window tables of VK-constant G1 bases (once per VK)
+__global__ void k_g1_fixed_tables(const G1Aff* bases, G1Aff* table) {
   int b = blockIdx.x, w = threadIdx.x;
   if (w >= BN_IC_WINDOWS) return;
-  groth16_ic_table_slice(table + ((size_t)b * BN_IC_WINDOWS + w) * BN_IC_ENTRIES, vk->ic[b + 1], w);
+  groth16_ic_table_slice(table + ((size_t)b * BN_IC_WINDOWS + w) * BN_IC_ENTRIES, bases[b], w);
 }
 
 __global__ void k_plonk_vk_prepare(PlonkVkDev* vk) {
   if (blockIdx.x == 0 && threadIdx.x == 0) plonk_vk_prepare(*vk);
 }
 
-template <int TPB>
-__global__ void __launch_bounds__(TPB, 1)
-    k_plonk_verify(const PlonkVkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride,
-                   const uint32_t* __restrict__ proof_len, const uint8_t* __restrict__ inputs, int n_inputs,
-                   const uint8_t* __restrict__ rnd, size_t n, uint8_t* __restrict__ status, uint8_t* dbg_g1,
-                   uint8_t* dbg_fr, uint8_t* dbg_m, uint8_t* dbg_gt) {
+// ---- PlonK, staged (plonk.cuh): A (per proof) -> terms 0 (per proof x term) -> C (per survivor) -> terms 1 -> E.
+// `list` holds the indices of the proofs that are still alive after stage A (early rejects cost nothing further);
+// a slot is set to -1 when a later stage ends the proof.
+struct PlonkDbgPtrs {
+  uint8_t *g1, *fr, *m, *gt;
+};
+__device__ __forceinline__ PlonkDebug plonk_dbg(const PlonkDbgPtrs& d, size_t i) {
+  return PlonkDebug{d.g1 ? d.g1 + 256 * i : nullptr, d.fr ? d.fr + 256 * i : nullptr, d.m ? d.m + 384 * i : nullptr,
+                    d.gt ? d.gt + 384 * i : nullptr};
+}
+
+__global__ void __launch_bounds__(64)
+    k_plonk_stage_a(const PlonkVkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride,
+                    const uint32_t* __restrict__ proof_len, const uint8_t* __restrict__ inputs, int n_inputs, size_t n,
+                    uint8_t* __restrict__ status, PlonkWork* work, int* list, int* count, PlonkDbgPtrs dp) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  PlonkDebug dbg{dbg_g1 ? dbg_g1 + 256 * i : nullptr, dbg_fr ? dbg_fr + 256 * i : nullptr,
-                 dbg_m ? dbg_m + 384 * i : nullptr, dbg_gt ? dbg_gt + 384 * i : nullptr};
   uint32_t len = proof_len ? proof_len[i] : (uint32_t)stride;
   if (len > stride) len = (uint32_t)stride;
-  status[i] = (uint8_t)plonk_verify_one(*vk, proofs + stride * i, len, inputs + (size_t)32 * n_inputs * i, n_inputs,
-                                        rnd + 32 * i, dbg);
+  int st = plonk_stage_a(work[i], *vk, proofs + stride * i, len, inputs + (size_t)32 * n_inputs * i, n_inputs,
+                         plonk_dbg(dp, i));
+  if (st == BN254V_OK_TRUE) {
+    list[atomicAdd(count, 1)] = (int)i;
+    status[i] = BN254V_STATUS_UNSET;
+  } else {
+    status[i] = (uint8_t)st;
+  }
+}
+
+__global__ void __launch_bounds__(64)
+    k_plonk_terms(const PlonkVkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride, PlonkWork* work,
+                  const int* __restrict__ list, const int* __restrict__ count, int stage) {
+  int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= *count) return;
+  int i = list[slot];
+  if (i < 0) return;
+  plonk_term(work[i], *vk, proofs + stride * (size_t)i, stage, blockIdx.y);
+}
+
+__global__ void __launch_bounds__(64)
+    k_plonk_stage_c(const PlonkVkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride,
+                    const uint8_t* __restrict__ rnd, uint8_t* __restrict__ status, PlonkWork* work, int* list,
+                    const int* __restrict__ count, PlonkDbgPtrs dp) {
+  int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= *count) return;
+  int i = list[slot];
+  int st = plonk_stage_c(work[i], *vk, proofs + stride * (size_t)i, rnd + (size_t)32 * i, plonk_dbg(dp, i));
+  if (st != BN254V_OK_TRUE) {
+    status[i] = (uint8_t)st;
+    list[slot] = -1;
+  }
+}
+
+template <int TPB>
+__global__ void __launch_bounds__(TPB, 1)
+    k_plonk_stage_e(const PlonkVkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride,
+                    uint8_t* __restrict__ status, PlonkWork* work, const int* __restrict__ list,
+                    const int* __restrict__ count, PlonkDbgPtrs dp) {
+  int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= *count) return;
+  int i = list[slot];
+  if (i < 0) return;
+  status[i] = (uint8_t)plonk_stage_e(work[i], *vk, proofs + stride * (size_t)i, plonk_dbg(dp, i));
 }
 
 template <int KP, int TPB>
@@ -285,6 +386,7 @@ void bn254v_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   for (auto& d : g_devs) {
     cudaSetDevice(d.id);
+    DevBuf::pool_release(d.id);
     cudaStreamDestroy(d.stream);
     cudaEventDestroy(d.ev0);
     cudaEventDestroy(d.ev1);
@@ -357,7 +459,7 @@ int bn254v_groth16_vk_load(const uint8_t* vk_bytes, size_t len, int sign_mode, b
       k_groth16_vk_prepare<<<1, 32, 0, d.stream>>>(dv);
       g_launches++;
       if (n_bases > 0) {
-        k_groth16_ic_tables<<<n_bases, BN_IC_WINDOWS, 0, d.stream>>>(dv, table);
+        k_g1_fixed_tables<<<n_bases, BN_IC_WINDOWS, 0, d.stream>>>(&dv->ic[1], table);
         g_launches++;
       }
       e = cudaGetLastError();
@@ -418,18 +520,32 @@ int bn254v_plonk_vk_load(const uint8_t* vk_bytes, size_t len, bn254v_vk** out) {
   bn254v_vk* vk = new bn254v_vk();
   vk->kind = 1;
   vk->n_public = hv->n_public;
+  vk->n_qcp = hv->n_qcp;
   vk->sign_mode = 0;
   for (auto& d : g_devs) {
     cudaError_t e = cudaSetDevice(d.id);
     PlonkVkDev* dv = nullptr;
     if (e == cudaSuccess) e = cudaMalloc(&dv, sizeof(PlonkVkDev));
+    // fixed-base window tables of the VK-constant MSM bases: [bases | tables] in one allocation
+    const int n_fixed = BN_PLONK_N_FIXED(hv->n_qcp);
+    G1Aff* tab_mem = nullptr;
+    if (e == cudaSuccess)
+      e = cudaMalloc(&tab_mem, sizeof(G1Aff) * ((size_t)n_fixed + (size_t)n_fixed * BN_IC_WINDOWS * BN_IC_ENTRIES));
+    if (e == cudaSuccess) {
+      std::vector<G1Aff> bases(n_fixed);
+      for (int i = 0; i < n_fixed; i++) bases[i] = plonk_fixed_base(*hv, i);
+      e = cudaMemcpy(tab_mem, bases.data(), sizeof(G1Aff) * n_fixed, cudaMemcpyHostToDevice);
+    }
+    hv->fixed_tables = tab_mem ? tab_mem + n_fixed : nullptr;
     if (e == cudaSuccess) e = cudaMemcpyAsync(dv, hv, sizeof(PlonkVkDev), cudaMemcpyHostToDevice, d.stream);
     if (e == cudaSuccess) {
       k_plonk_vk_prepare<<<1, 32, 0, d.stream>>>(dv);
-      g_launches++;
+      k_g1_fixed_tables<<<n_fixed, BN_IC_WINDOWS, 0, d.stream>>>(tab_mem, tab_mem + n_fixed);
+      g_launches += 2;
       e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+    vk->aux.push_back(tab_mem);
     if (e != cudaSuccess) {
       delete hv;
       bn254v_vk_free(vk);
@@ -519,7 +635,7 @@ int bn254v_plonk_verify_batch(const bn254v_vk* vk, const uint8_t* proofs, size_t
   if (n == 0) return BN254V_SUCCESS;
   const int nd = (int)g_devs.size();
   struct Part {
-    DevBuf proofs, lens, inputs, rnd, status, g1, fr, m, gt;
+    DevBuf proofs, lens, inputs, rnd, status, g1, fr, m, gt, work, list, count;
   };
   std::vector<Part> parts(nd);
   const size_t in_bytes = (size_t)32 * n_inputs;
@@ -551,19 +667,45 @@ int bn254v_plonk_verify_batch(const bn254v_vk* vk, const uint8_t* proofs, size_t
     if (p.fr.p) CU(cudaMemsetAsync(p.fr.p, 0, m * 256, dev.stream));
     if (p.m.p) CU(cudaMemsetAsync(p.m.p, 0, m * 384, dev.stream));
     if (p.gt.p) CU(cudaMemsetAsync(p.gt.p, 0, m * 384, dev.stream));
-#define LAUNCH_PK(TPB)                                                                                            \
-  k_plonk_verify<TPB><<<(unsigned)((m + TPB - 1) / TPB), TPB, 0, dev.stream>>>(                                  \
-      (const PlonkVkDev*)vk->dev[d], p.proofs.as<uint8_t>(), proof_stride, proof_len ? p.lens.as<uint32_t>() : nullptr, \
-      p.inputs.as<uint8_t>(), n_inputs, p.rnd.as<uint8_t>(), m, p.status.as<uint8_t>(), p.g1.as<uint8_t>(),        \
-      p.fr.as<uint8_t>(), p.m.as<uint8_t>(), p.gt.as<uint8_t>())
-    switch (pick_shape(m)) {
-      case 3: case 4: LAUNCH_PK(448); break;
-      case 6: LAUNCH_PK(32); break;
-      default: LAUNCH_PK(128); break;
+    {
+      // chunks bound the per-proof workspace (PlonkWork, ~1.9 KB): 2^16 proofs -> 125 MB
+      const size_t CH = 1u << 16;
+      const size_t mc = m < CH ? m : CH;
+      DevBuf &work = p.work, &list = p.list, &count = p.count;  // live until the final synchronisation
+      CU(work.alloc(mc * sizeof(PlonkWork)));
+      CU(list.alloc(mc * sizeof(int)));
+      CU(count.alloc(sizeof(int)));
+      const PlonkVkDev* dvk = (const PlonkVkDev*)vk->dev[d];
+      for (size_t c0 = 0; c0 < m; c0 += CH) {
+        const size_t cm = m - c0 < CH ? m - c0 : CH;
+        const uint8_t* cp = p.proofs.as<uint8_t>() + c0 * proof_stride;
+        PlonkDbgPtrs dp{p.g1.p ? p.g1.as<uint8_t>() + c0 * 256 : nullptr, p.fr.p ? p.fr.as<uint8_t>() + c0 * 256 : nullptr,
+                        p.m.p ? p.m.as<uint8_t>() + c0 * 384 : nullptr, p.gt.p ? p.gt.as<uint8_t>() + c0 * 384 : nullptr};
+        uint8_t* cst = p.status.as<uint8_t>() + c0;
+        const unsigned g64 = (unsigned)((cm + 63) / 64);
+        const int n_terms = vk->n_qcp + 10;
+        CU(cudaMemsetAsync(count.p, 0, sizeof(int), dev.stream));
+        k_plonk_stage_a<<<g64, 64, 0, dev.stream>>>(dvk, cp, proof_stride, proof_len ? p.lens.as<uint32_t>() + c0 : nullptr,
+                                                    p.inputs.as<uint8_t>() + c0 * in_bytes, n_inputs, cm, cst,
+                                                    work.as<PlonkWork>(), list.as<int>(), count.as<int>(), dp);
+        k_plonk_terms<<<dim3(g64, n_terms), 64, 0, dev.stream>>>(dvk, cp, proof_stride, work.as<PlonkWork>(),
+                                                                 list.as<int>(), count.as<int>(), 0);
+        k_plonk_stage_c<<<g64, 64, 0, dev.stream>>>(dvk, cp, proof_stride, p.rnd.as<uint8_t>() + c0 * 32, cst,
+                                                    work.as<PlonkWork>(), list.as<int>(), count.as<int>(), dp);
+        k_plonk_terms<<<dim3(g64, n_terms), 64, 0, dev.stream>>>(dvk, cp, proof_stride, work.as<PlonkWork>(),
+                                                                 list.as<int>(), count.as<int>(), 1);
+        if (pick_shape(cm) == 6)
+          k_plonk_stage_e<32><<<(unsigned)((cm + 31) / 32), 32, 0, dev.stream>>>(dvk, cp, proof_stride, cst,
+                                                                                 work.as<PlonkWork>(), list.as<int>(),
+                                                                                 count.as<int>(), dp);
+        else
+          k_plonk_stage_e<128><<<(unsigned)((cm + 127) / 128), 128, 0, dev.stream>>>(dvk, cp, proof_stride, cst,
+                                                                                     work.as<PlonkWork>(), list.as<int>(),
+                                                                                     count.as<int>(), dp);
+        g_launches += 5;
+        CU(cudaGetLastError());
+      }
     }
-#undef LAUNCH_PK
-    g_launches++;
-    CU(cudaGetLastError());
     CU(cudaMemcpyAsync(status + lo, p.status.p, m, cudaMemcpyDeviceToHost, dev.stream));
     if (p.g1.p) CU(cudaMemcpyAsync(dbg->g1_out + lo * 256, p.g1.p, m * 256, cudaMemcpyDeviceToHost, dev.stream));
     if (p.fr.p) CU(cudaMemcpyAsync(dbg->fr_out + lo * 256, p.fr.p, m * 256, cudaMemcpyDeviceToHost, dev.stream));

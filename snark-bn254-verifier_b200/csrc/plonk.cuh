@@ -9,6 +9,7 @@
 // VK-constant work is hoisted to vk_load: the SHA-256 state after the VK prefix of the gamma transcript,
 // omega^(nPub + cci), the canonical bytes of S1/S2/Qcp hashed by the KZG transcript and the two G2 line tables.
 #pragma once
+#include "groth16.cuh"
 #include "io.cuh"
 #include "pairing.cuh"
 #include "sha256.cuh"
@@ -29,8 +30,25 @@ struct PlonkVkDev {
   G2Aff g2[2];
   Sha256 gamma_prefix;                       // state after "gamma" | S1 S2 S3 Ql Qr Qm Qo Qk | Qcp..
   uint8_t kzg_vk_bytes[64 * (2 + BN_MAX_QCP)];  // canonical S1 | S2 | Qcp..  (KZG transcript)
+  const G1Aff* fixed_tables;                 // [7 + n_qcp + 1][32][255] window tables of the VK bases, or null
   Line g2_lines[2][BN_N_LINES];
 };
+
+// VK-constant MSM bases, in table order: Ql Qr Qm Qo S3 S1 S2 Qcp.. g1(KZG)
+#define BN_PLONK_N_FIXED(nq) (8 + (nq))
+HD const G1Aff& plonk_fixed_base(const PlonkVkDev& vk, int idx) {
+  switch (idx) {
+    case 0: return vk.ql;
+    case 1: return vk.qr;
+    case 2: return vk.qm;
+    case 3: return vk.qo;
+    case 4: return vk.s[2];
+    case 5: return vk.s[0];
+    case 6: return vk.s[1];
+  }
+  if (idx < 7 + vk.n_qcp) return vk.qcp[idx - 7];
+  return vk.g1;
+}
 
 HD void plonk_vk_prepare(PlonkVkDev& vk) {
   g2_precompute(vk.g2_lines[0], vk.g2[0]);
@@ -74,11 +92,31 @@ HD uint32_t be32_at(const uint8_t* b) {
   return ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
 }
 
-// acc += [k] P   (k Montgomery); AffineG1::msm is a plain sum of scalar multiples
-HDN void msm_acc(G1Jac& acc, const G1Aff& p, const Fr& k_mont) {
-  Fr k = fe_from_mont(k_mont);
-  G1Jac t = scalar_mul(p, k.v);
-  acc = jac_add(acc, t);
+// [k] P for a proof-supplied point: fixed 4-bit windows over a 15-entry table (uniform control flow across the
+// threads of a warp, unlike bit-by-bit double-and-add).  k: plain 8 x u32 LE.  Same group element as the reference's
+// AffineG1 * Fr; AffineG1::msm is a plain sum of such terms.
+HDN G1Jac g1_mul_w4(const G1Aff& p, const uint32_t* k) {
+  G1Jac tab[15];
+  tab[0] = to_jac(p);
+  tab[1] = jac_double(tab[0]);
+  for (int i = 2; i < 15; i++) tab[i] = jac_add_mixed(tab[i - 1], p);
+  G1Jac acc = jac_identity<Fp>();
+  for (int w = 63; w >= 0; w--) {
+    if (w != 63)
+      for (int j = 0; j < 4; j++) acc = jac_double(acc);
+    uint32_t d = (k[w >> 3] >> (4 * (w & 7))) & 15;
+    if (d) acc = jac_add(acc, tab[d - 1]);
+  }
+  return acc;
+}
+// [k] B for a VK-constant base with a window table T[w][d-1] = d * 2^(8w) * B (see groth16.cuh)
+HDN G1Jac g1_mul_fixed(const G1Aff* tab, const uint32_t* k) {
+  G1Jac acc = jac_identity<Fp>();
+  for (int w = 0; w < BN_IC_WINDOWS; w++) {
+    uint32_t d = (k[w >> 2] >> (8 * (w & 3))) & 0xff;
+    if (d) acc = jac_add_mixed(acc, tab[w * BN_IC_ENTRIES + (d - 1)]);
+  }
+  return acc;
 }
 
 // SHA-256 transcript pieces
@@ -125,8 +163,36 @@ struct PlonkDebug {
   uint8_t* gt;      // 384
 };
 
-HD int plonk_verify_one(const PlonkVkDev& vk, const uint8_t* pr, uint32_t len, const uint8_t* inputs_be, int n_inputs,
-                        const uint8_t* rnd_be, const PlonkDebug& dbg) {
+// ---------------------------------------------------------------------------------------------------------------
+// The verification is cut into stages so that the MSM terms -- where a PlonK verification spends its time -- can
+// run one term per thread (k_plonk_terms) while the sequential parts run one proof per thread:
+//   stage A  parse + validate, Fiat-Shamir challenges, Fr pipeline, const_lin check    -> scalars of the 10+nQcp
+//            terms of the linearised-polynomial MSM                                   (early rejects stop here)
+//   terms 0  one scalar multiplication per (proof, term)
+//   stage C  sum -> linearised digest (affine, hashed), KZG gamma, folded evaluation    -> scalars of the 5+nQcp
+//            fold terms and the 5 terms of batch_verify_multi_points
+//   terms 1  one scalar multiplication per (proof, term)
+//   stage E  sums with the reference's identity checks, 2-pair Miller loop, final exponentiation, verdict
+// plonk_verify_one() runs the same stage functions back to back in one thread (host simulation, tiny batches).
+// ---------------------------------------------------------------------------------------------------------------
+#define BN_PLONK_MAX_T (BN_MAX_QCP + 10)
+
+struct PlonkWork {
+  uint32_t sc[BN_PLONK_MAX_T][8];  // plain scalars of the current stage's terms
+  G1Jac part[BN_PLONK_MAX_T];      // term results of the current stage
+  Fr zeta;                         // Montgomery
+  G1Aff lin;                       // linearised polynomial digest
+};
+HD int plonk_n_terms(const PlonkVkDev& vk, int stage) { return vk.n_qcp + 10; }  // both stages: nQcp + 10
+
+HD void plonk_put_scalar(PlonkWork& w, int t, const Fr& k_mont) {
+  Fr k = fe_from_mont(k_mont);
+#pragma unroll
+  for (int i = 0; i < 8; i++) w.sc[t][i] = k.v[i];
+}
+
+HD int plonk_stage_a(PlonkWork& w, const PlonkVkDev& vk, const uint8_t* pr, uint32_t len, const uint8_t* inputs_be,
+                     int n_inputs, const PlonkDebug& dbg) {
   // ---- public inputs are bn::Fr in the reference's API: a value >= r cannot be constructed by the caller
   for (int i = 0; i < n_inputs; i++) {
     Fr t;
@@ -134,9 +200,9 @@ HD int plonk_verify_one(const PlonkVkDev& vk, const uint8_t* pr, uint32_t len, c
   }
   // ---- load_plonk_proof_from_bytes (plonk/converter.rs:121-178)
   if (len < 516) return BN254V_PANIC_SHORT_BUFFER;
-  G1Aff P8[8];  // L R O Z H0 H1 H2 batchedH
-  for (int i = 0; i < 8; i++) {
-    int st = load_g1_checked(P8[i], pr + 64 * i);
+  for (int i = 0; i < 8; i++) {  // L R O Z H0 H1 H2 batchedH
+    G1Aff t;
+    int st = load_g1_checked(t, pr + 64 * i);
     if (st != BN254V_OK_TRUE) return st;
   }
   uint32_t ncl = be32_at(pr + 512);
@@ -150,10 +216,9 @@ HD int plonk_verify_one(const PlonkVkDev& vk, const uint8_t* pr, uint32_t len, c
     off += 32;
   }
   if ((uint64_t)off + 100 > len) return BN254V_PANIC_SHORT_BUFFER;
-  const uint32_t off_zsh = off;
-  G1Aff zs_h;
   {
-    int st = load_g1_checked(zs_h, pr + off);
+    G1Aff t;
+    int st = load_g1_checked(t, pr + off);  // z-shifted opening proof H
     if (st != BN254V_OK_TRUE) return st;
   }
   Fr zu;
@@ -161,13 +226,11 @@ HD int plonk_verify_one(const PlonkVkDev& vk, const uint8_t* pr, uint32_t len, c
   uint32_t nbsb = be32_at(pr + off + 96);
   off += 100;
   const uint32_t off_bsb = off;
-  G1Aff bsb[BN_MAX_QCP];
   for (uint32_t i = 0; i < nbsb; i++) {
     if ((uint64_t)off + 64 > len) return BN254V_PANIC_SHORT_BUFFER;
     G1Aff t;
     int st = load_g1_checked(t, pr + off);
     if (st != BN254V_OK_TRUE) return st;
-    if (i < BN_MAX_QCP) bsb[i] = t;
     off += 64;
   }
   // ---- verify_plonk shape checks (plonk/verify.rs:52-59)
@@ -199,6 +262,7 @@ HD int plonk_verify_one(const PlonkVkDev& vk, const uint8_t* pr, uint32_t len, c
   sha256_update(sh, pr + 256, 192);  // H0 H1 H2
   sha256_final(sh, dg);
   Fr zeta = fr_from_be_mod_order(dg);
+  w.zeta = zeta;
 
   // ---- zeta^n - 1, L_1(zeta), PI(zeta) (plonk/verify.rs:98-163); one shared inversion (Montgomery's trick) for
   //      (zeta-1), the public-input denominators and the BSB22 denominators: the inverses are the same field elements.
@@ -241,9 +305,9 @@ HD int plonk_verify_one(const PlonkVkDev& vk, const uint8_t* pr, uint32_t len, c
   {
     Fr accw = one;
     for (int i = 0; i < n_inputs; i++) {
-      Fr w;
-      fr_load_be(w, inputs_be + 32 * i);
-      Fr li = fr_mul(fr_mul(fr_mul(fr_mul(zh_zeta, dens[1 + i]), vk.size_inv), accw), w);
+      Fr x;
+      fr_load_be(x, inputs_be + 32 * i);
+      Fr li = fr_mul(fr_mul(fr_mul(fr_mul(zh_zeta, dens[1 + i]), vk.size_inv), accw), x);
       accw = fr_mul(accw, vk.generator);
       pi = fr_add(pi, li);
     }
@@ -273,7 +337,7 @@ HD int plonk_verify_one(const PlonkVkDev& vk, const uint8_t* pr, uint32_t len, c
   // A claimed-value count other than 6 + nQcp reaches fold_proof's length check after the linearisation MSM.
   if ((int)ncl != 6 + vk.n_qcp) return BN254V_ERR_INVALID_NUMBER_OF_DIGESTS;
 
-  // ---- linearised polynomial digest (plonk/verify.rs:218-284)
+  // ---- scalars of the linearised polynomial digest (plonk/verify.rs:218-284)
   Fr s1c = fr_mul(fr_mul(fr_mul(fr_mul(t1, t2), beta), alpha), zu);  // (b s1 + l + g)(b s2 + r + g) b a zu
   const Fr& u = vk.coset_shift;
   Fr bz = fr_mul(beta, zeta);
@@ -281,89 +345,141 @@ HD int plonk_verify_one(const PlonkVkDev& vk, const uint8_t* pr, uint32_t len, c
   Fr s2c = fr_mul(fr_mul(fr_add(fr_add(bz, gamma), l), fr_add(fr_add(buz, gamma), r)),
                   fr_add(fr_add(fr_mul(buz, u), gamma), o));
   s2c = fr_neg(fr_mul(s2c, alpha));
-  Fr coeff_z = fr_add(a2l1, s2c);
-  Fr rl = fr_mul(l, r);
   Fr zn2 = fr_mul(fr_mul(zeta_n, zeta), zeta);  // zeta^(n+2)
-  Fr zn2zh = fr_neg(fr_mul(zn2, zh_zeta));
-  Fr zn2sqzh = fr_neg(fr_mul(fr_mul(zn2, zn2), zh_zeta));
-  Fr zh = fr_neg(zh_zeta);
+  // term order: BSB22[i] * claimed[6+i] | Ql*l Qr*r Qm*rl Qo*o Qk*1 S3*s1c | Z*coeff_z H0*zh H1*zn2zh H2*zn2sqzh
+  int t = 0;
+  for (int i = 0; i < vk.n_qcp; i++) plonk_put_scalar(w, t++, cl[6 + i]);
+  plonk_put_scalar(w, t++, l);
+  plonk_put_scalar(w, t++, r);
+  plonk_put_scalar(w, t++, fr_mul(l, r));
+  plonk_put_scalar(w, t++, o);
+  plonk_put_scalar(w, t++, one);
+  plonk_put_scalar(w, t++, s1c);
+  plonk_put_scalar(w, t++, fr_add(a2l1, s2c));
+  plonk_put_scalar(w, t++, fr_neg(zh_zeta));
+  plonk_put_scalar(w, t++, fr_neg(fr_mul(zn2, zh_zeta)));
+  plonk_put_scalar(w, t++, fr_neg(fr_mul(fr_mul(zn2, zn2), zh_zeta)));
+  return BN254V_OK_TRUE;
+}
 
-  G1Jac acc = jac_identity<Fp>();
-  for (int i = 0; i < vk.n_qcp; i++) msm_acc(acc, bsb[i], cl[6 + i]);
-  msm_acc(acc, vk.ql, l);
-  msm_acc(acc, vk.qr, r);
-  msm_acc(acc, vk.qm, rl);
-  msm_acc(acc, vk.qo, o);
-  acc = jac_add_mixed(acc, vk.qk);  // scalar 1
-  msm_acc(acc, vk.s[2], s1c);
-  msm_acc(acc, P8[3], coeff_z);
-  msm_acc(acc, P8[4], zh);
-  msm_acc(acc, P8[5], zn2zh);
-  msm_acc(acc, P8[6], zn2sqzh);
-  G1Aff lin;
-  if (!to_affine(lin, acc)) return BN254V_PANIC_IDENTITY;
+// offsets of the tail of a well-formed proof (6 + nQcp claimed values; survivors of stage A only)
+HD uint32_t plonk_off_zsh(const PlonkVkDev& vk) { return 516 + 32 * (6 + vk.n_qcp); }
+HD uint32_t plonk_off_bsb(const PlonkVkDev& vk) { return plonk_off_zsh(vk) + 100; }
+
+HD G1Jac plonk_fixed_or_var(const PlonkVkDev& vk, int base, const uint32_t* k) {
+  if (vk.fixed_tables) return g1_mul_fixed(vk.fixed_tables + (size_t)base * BN_IC_WINDOWS * BN_IC_ENTRIES, k);
+  return g1_mul_w4(plonk_fixed_base(vk, base), k);
+}
+HD G1Jac plonk_var(const uint8_t* pt_bytes, const uint32_t* k) {
+  G1Aff p;
+  load_g1_unchecked(p, pt_bytes);  // validated in stage A
+  return g1_mul_w4(p, k);
+}
+
+// One scalar multiplication: term `t` of stage 0 (linearised digest) or stage 1 (fold + batch opening).
+HD void plonk_term(PlonkWork& w, const PlonkVkDev& vk, const uint8_t* pr, int stage, int t) {
+  const uint32_t* k = w.sc[t];
+  const int nq = vk.n_qcp;
+  G1Jac res;
+  if (stage == 0) {
+    if (t < nq) res = plonk_var(pr + plonk_off_bsb(vk) + 64 * t, k);
+    else {
+      int j = t - nq;
+      if (j < 4) res = plonk_fixed_or_var(vk, j, k);           // Ql Qr Qm Qo
+      else if (j == 4) res = to_jac(vk.qk);                    // Qk * 1
+      else if (j == 5) res = plonk_fixed_or_var(vk, 4, k);     // S3
+      else res = plonk_var(pr + 192 + 64 * (j - 6), k);        // Z H0 H1 H2
+    }
+  } else {
+    if (t < 5 + nq) {
+      int i = t + 1;  // digest index: lin(0) L R O S1 S2 Qcp..
+      if (i <= 3) res = plonk_var(pr + 64 * (i - 1), k);
+      else res = plonk_fixed_or_var(vk, 5 + (i - 4), k);       // S1 S2 Qcp..
+    } else {
+      int j = t - (5 + nq);
+      if (j == 0) res = plonk_var(pr + plonk_off_zsh(vk), k);        // zsH * rnd
+      else if (j == 1) res = plonk_var(pr + 192, k);                 // Z * rnd
+      else if (j == 2) res = plonk_fixed_or_var(vk, 7 + nq, k);      // g1 * folded evals
+      else if (j == 3) res = plonk_var(pr + 448, k);                 // batchedH * zeta
+      else res = plonk_var(pr + plonk_off_zsh(vk), k);               // zsH * (rnd omega zeta)
+    }
+  }
+  w.part[t] = res;
+}
+
+HD int plonk_stage_c(PlonkWork& w, const PlonkVkDev& vk, const uint8_t* pr, const uint8_t* rnd_be,
+                     const PlonkDebug& dbg) {
+  const int nq = vk.n_qcp;
+  G1Jac acc = w.part[0];
+  for (int t = 1; t < nq + 10; t++) acc = jac_add(acc, w.part[t]);
+  if (!to_affine(w.lin, acc)) return BN254V_PANIC_IDENTITY;
   uint8_t lin_bytes[64];
-  store_g1(lin_bytes, lin);
+  store_g1(lin_bytes, w.lin);
   if (dbg.g1) memcpy(dbg.g1, lin_bytes, 64);
-
   // ---- kzg::fold_proof (plonk/kzg.rs:87-126): gamma_kzg = H("gamma" | zeta | digests | claimed | zu)
+  const uint32_t ncl = 6 + nq, off_zsh = plonk_off_zsh(vk);
+  Sha256 sh;
+  uint8_t dg[32], tmp32[32];
   sha256_init(sh);
   sha_bytes(sh, "gamma", 5);
-  uint8_t tmp32[32];
-  fr_store_be(tmp32, zeta);
+  fr_store_be(tmp32, w.zeta);
   sha256_update(sh, tmp32, 32);
   sha256_update(sh, lin_bytes, 64);
   sha256_update(sh, pr, 192);  // L R O
-  sha256_update(sh, vk.kzg_vk_bytes, 64 * (2 + vk.n_qcp));
+  sha256_update(sh, vk.kzg_vk_bytes, 64 * (2 + nq));
   sha256_update(sh, pr + 516, 32 * ncl);
   sha256_update(sh, pr + off_zsh + 64, 32);  // zu
   sha256_final(sh, dg);
   Fr kg = fr_from_be_mod_order(dg);
   if (dbg.fr) fr_store_be(dbg.fr + 128, kg);
-  // folded digest = sum gamma^i D_i, folded eval = sum gamma^i claimed_i;  D = lin, L, R, O, S1, S2, Qcp..
-  Fr gi = kg;
-  Fr folded_eval = cl[0];
-  G1Jac fd = to_jac(lin);
-  for (int i = 1; i < 6 + vk.n_qcp; i++) {
-    const G1Aff& D = i <= 3 ? P8[i - 1] : (i <= 5 ? vk.s[i - 4] : vk.qcp[i - 6]);
-    msm_acc(fd, D, gi);
-    folded_eval = fr_add(folded_eval, fr_mul(cl[i], gi));
+  // fold scalars gamma^i and folded evaluation sum gamma^i claimed_i
+  Fr gi = kg, folded_eval, c;
+  fr_load_be(folded_eval, pr + 516);
+  for (int i = 1; i < 6 + nq; i++) {
+    plonk_put_scalar(w, i - 1, gi);
+    fr_load_be(c, pr + 516 + 32 * i);
+    folded_eval = fr_add(folded_eval, fr_mul(c, gi));
     gi = fr_mul(gi, kg);
   }
+  // batch_verify_multi_points scalars: random numbers [1, rnd], points [zeta, omega zeta]
+  Fr rnd = fr_from_be_mod_order(rnd_be), zu;
+  fr_load_be(zu, pr + off_zsh + 64);
+  const int b = 5 + nq;
+  plonk_put_scalar(w, b + 0, rnd);
+  plonk_put_scalar(w, b + 1, rnd);
+  plonk_put_scalar(w, b + 2, fr_add(folded_eval, fr_mul(zu, rnd)));
+  plonk_put_scalar(w, b + 3, w.zeta);
+  plonk_put_scalar(w, b + 4, fr_mul(rnd, fr_mul(w.zeta, vk.generator)));
+  return BN254V_OK_TRUE;
+}
+
+HD int plonk_stage_e(PlonkWork& w, const PlonkVkDev& vk, const uint8_t* pr, const PlonkDebug& dbg) {
+  const int nq = vk.n_qcp, b = 5 + nq;
+  // folded digest = lin + sum gamma^i D_i (kzg::fold)
+  G1Jac fd = to_jac(w.lin);
+  for (int t = 0; t < b; t++) fd = jac_add(fd, w.part[t]);
   if (is_identity(fd)) return BN254V_PANIC_IDENTITY;
   if (dbg.g1) {
     G1Aff t;
     to_affine(t, fd);
     store_g1(dbg.g1 + 64, t);
   }
-
-  // ---- kzg::batch_verify_multi_points (plonk/kzg.rs:128-190): digests [folded, Z], proofs [(batchedH, folded_eval),
-  //      (zsH, zu)], points [zeta, omega zeta], random numbers [1, rnd]
-  Fr rnd = fr_from_be_mod_order(rnd_be);
-  G1Jac fq = to_jac(P8[7]);  // folded quotients = batchedH + rnd zsH
-  msm_acc(fq, zs_h, rnd);
+  // ---- kzg::batch_verify_multi_points (plonk/kzg.rs:128-190), with the reference's AffineG1 conversions (identity panics)
+  G1Aff bh;
+  load_g1_unchecked(bh, pr + 448);
+  G1Jac fq = jac_add_mixed(w.part[b + 0], bh);  // folded quotients = batchedH + rnd zsH
   if (is_identity(fq)) return BN254V_PANIC_IDENTITY;
-  G1Jac fdg = fd;  // folded digests = folded + rnd Z
-  msm_acc(fdg, P8[3], rnd);
+  G1Jac fdg = jac_add(fd, w.part[b + 1]);       // folded digests = folded + rnd Z
   if (is_identity(fdg)) return BN254V_PANIC_IDENTITY;
-  Fr fev = fr_add(folded_eval, fr_mul(zu, rnd));
-  {
-    Fr k = fe_from_mont(fev);
-    G1Jac fec = scalar_mul(vk.g1, k.v);  // vk.g1 * folded_evals, .into() AffineG1
-    if (is_identity(fec)) return BN254V_PANIC_IDENTITY;
-    fec.y = neg(fec.y);
-    fdg = jac_add(fdg, fec);
-    if (is_identity(fdg)) return BN254V_PANIC_IDENTITY;
-  }
-  {
-    Fr shifted = fr_mul(zeta, vk.generator);
-    G1Jac fpq = jac_identity<Fp>();
-    msm_acc(fpq, P8[7], zeta);
-    msm_acc(fpq, zs_h, fr_mul(rnd, shifted));
-    if (is_identity(fpq)) return BN254V_PANIC_IDENTITY;
-    fdg = jac_add(fdg, fpq);
-    if (is_identity(fdg)) return BN254V_PANIC_IDENTITY;
-  }
+  G1Jac fec = w.part[b + 2];                    // vk.g1 * folded evals
+  if (is_identity(fec)) return BN254V_PANIC_IDENTITY;
+  fec.y = neg(fec.y);
+  fdg = jac_add(fdg, fec);
+  if (is_identity(fdg)) return BN254V_PANIC_IDENTITY;
+  G1Jac fpq = jac_add(w.part[b + 3], w.part[b + 4]);  // zeta batchedH + rnd omega zeta zsH
+  if (is_identity(fpq)) return BN254V_PANIC_IDENTITY;
+  fdg = jac_add(fdg, fpq);
+  if (is_identity(fdg)) return BN254V_PANIC_IDENTITY;
   fq.y = neg(fq.y);
   G1Aff pf[2];
   to_affine(pf[0], fdg);
@@ -379,6 +495,19 @@ HD int plonk_verify_one(const PlonkVkDev& vk, const uint8_t* pr, uint32_t len, c
   final_exponentiation(f, f);
   if (dbg.gt) fp12_to_bytes(dbg.gt, f);
   return eq(f, fp12_one()) ? BN254V_OK_TRUE : BN254V_ERR_PAIRING_CHECK_FAILED;
+}
+
+// All stages in one thread.
+HD int plonk_verify_one(const PlonkVkDev& vk, const uint8_t* pr, uint32_t len, const uint8_t* inputs_be, int n_inputs,
+                        const uint8_t* rnd_be, const PlonkDebug& dbg) {
+  PlonkWork w;
+  int st = plonk_stage_a(w, vk, pr, len, inputs_be, n_inputs, dbg);
+  if (st != BN254V_OK_TRUE) return st;
+  for (int t = 0; t < vk.n_qcp + 10; t++) plonk_term(w, vk, pr, 0, t);
+  st = plonk_stage_c(w, vk, pr, rnd_be, dbg);
+  if (st != BN254V_OK_TRUE) return st;
+  for (int t = 0; t < vk.n_qcp + 10; t++) plonk_term(w, vk, pr, 1, t);
+  return plonk_stage_e(w, vk, pr, dbg);
 }
 
 }  // namespace bn254

@@ -124,7 +124,20 @@ void* hs_plonk_vk_new(const uint8_t* vk_bytes, size_t len) {
   plonk_vk_prepare(*hv);
   return hv;
 }
-void hs_plonk_vk_free(void* vk) { delete (PlonkVkDev*)vk; }
+// attach the fixed-base window tables the CUDA vk_load builds (slow on the host: ~75 k affine conversions)
+void hs_plonk_vk_add_tables(void* vkp) {
+  PlonkVkDev* vk = (PlonkVkDev*)vkp;
+  const int nf = BN_PLONK_N_FIXED(vk->n_qcp);
+  G1Aff* tab = new G1Aff[(size_t)nf * BN_IC_WINDOWS * BN_IC_ENTRIES];
+  for (int b = 0; b < nf; b++)
+    for (int w = 0; w < BN_IC_WINDOWS; w++)
+      groth16_ic_table_slice(tab + ((size_t)b * BN_IC_WINDOWS + w) * BN_IC_ENTRIES, plonk_fixed_base(*vk, b), w);
+  vk->fixed_tables = tab;
+}
+void hs_plonk_vk_free(void* vk) {
+  delete[] ((PlonkVkDev*)vk)->fixed_tables;
+  delete (PlonkVkDev*)vk;
+}
 int hs_plonk_verify(void* vk, const uint8_t* proof, uint32_t len, const uint8_t* inputs, int n_inputs, const uint8_t* rnd,
                     uint8_t* g1, uint8_t* fr, uint8_t* miller, uint8_t* gt) {
   PlonkDebug dbg{g1, fr, miller, gt};

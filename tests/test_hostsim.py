@@ -143,6 +143,24 @@ def test_plonk_fixtures_bit_exact(hs):
     hs.hs_plonk_vk_free(vk)
 
 
+def test_plonk_fixed_base_tables_give_the_same_points(hs):
+    """Same fixture through the VK-constant window tables (what the CUDA vk_load builds): identical digests / GT."""
+    from helpers import plonk_fixture
+    vk = _hs_plonk(hs)
+    hs.hs_plonk_vk_add_tables.argtypes = [ctypes.c_void_p]
+    hs.hs_plonk_vk_add_tables(vk)
+    g = load_json("plonk_golden.json")["sha2"]
+    pr, xs = plonk_fixture("sha2")
+    inputs = b"".join(x.to_bytes(32, "big") for x in xs)
+    g1, fr, ml, gt = (ctypes.create_string_buffer(n) for n in (256, 256, 384, 384))
+    st = hs.hs_plonk_verify(vk, pr, len(pr), inputs, 2, int(g["rnd"], 16).to_bytes(32, "big"), g1, fr, ml, gt)
+    assert st == 0
+    assert g1.raw[0:64] == pt_bytes(g["lin_digest"]) and g1.raw[64:128] == pt_bytes(g["folded_digest"])
+    assert g1.raw[128:192] == pt_bytes(g["pair_g1"][0]) and g1.raw[192:256] == pt_bytes(g["pair_g1"][1])
+    assert ml.raw.hex() == g["miller"] and gt.raw.hex() == g["gt"]
+    hs.hs_plonk_vk_free(vk)
+
+
 def test_plonk_mutations_and_structural_cases(hs):
     from helpers import PLONK_STATUS, oracle_plonk_status, plonk_structural_suite, plonk_vk_bytes
     vk = _hs_plonk(hs)
