@@ -291,7 +291,7 @@ def run_b200(args):
         return
 
     work = work_per_proof()
-    macs_per_proof = work["groth16_fp_mul"] * MACS_PER_FPMUL
+    macs_per_proof = work.get("groth16_macs", work["groth16_fp_mul"] * MACS_PER_FPMUL)
     achieved = macs_per_proof * n * args.steps / (sum(kernel_ms) * 1e-3)  # this rank's kernel
     roofline = {
         "bound": "int32-imad", "achieved": achieved / 1e12, "peak": peak["wide_mac_per_s"] / 1e12, "unit": "TMAC/s",

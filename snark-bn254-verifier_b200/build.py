@@ -10,7 +10,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libbn254v.so")
+LIB = os.environ.get("BN254V_LIB") or os.path.join(HERE, "libbn254v.so")  # BN254V_LIB: experiment builds
 SOURCES = [os.path.join(CSRC, "bn254v.cu")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

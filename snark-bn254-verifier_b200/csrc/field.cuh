@@ -36,6 +36,11 @@
 #else
 #define BN_PHASE_SYNC()
 #endif
+#ifdef BN_SYNC_FINE  // measured on B200: the per-iteration barrier alone is 3 % faster than barriers between all big operations
+#define BN_PHASE_SYNC_FINE() BN_PHASE_SYNC()  // between the big operations inside one loop iteration
+#else
+#define BN_PHASE_SYNC_FINE()
+#endif
 
 namespace bn254 {
 
@@ -274,19 +279,128 @@ HD Fe<C> fe_mul_inl(const Fe<C>& a, const Fe<C>& b) {
 // call costs ~20 register moves against ~190 instructions of multiplier, and keeps the pairing
 // kernels' code small enough for the instruction cache.
 #if !defined(__CUDA_ARCH__) && defined(BN254_COUNT_MULS)
-// host-simulation builds only: counts field multiplications (the algorithmic work unit of DESIGN.md)
-inline unsigned long long& fe_mul_counter() {
+// host-simulation builds only: counts 32x32+64 limb multiply-adds (the algorithmic work unit of DESIGN.md):
+// 136 per Montgomery multiplication, 64 per wide product, 72 per wide reduction
+inline unsigned long long& fe_mac_counter() {
   static thread_local unsigned long long c = 0;
   return c;
 }
-#define BN_COUNT_MUL() (fe_mul_counter()++)
+#define BN_COUNT_MACS(n) (fe_mac_counter() += (n))
 #else
-#define BN_COUNT_MUL()
+#define BN_COUNT_MACS(n)
 #endif
+
+// ---------------------------------------------------------------------------------------------
+// Lazy reduction building blocks (used by the Fp2 multiplication): a full 512-bit product without reduction,
+// and a Montgomery reduction of a 512-bit value.  Fp2 Karatsuba then needs 3 products + 2 reductions
+// (3*64 + 2*72 = 336 multiply-adds) instead of 3 full Montgomery multiplications (408).
+// ---------------------------------------------------------------------------------------------
+// T[0..15] = a * b (plain integer product).  Products a_j * b_i whose position i+j is even accumulate in E, the others
+// in O, so every 64-bit product lands on an aligned word pair of its accumulator (one IMAD.WIDE.U32 each); the
+// carry out of a row's chain falls on a word that is either still zero or holds earlier carries (<= 2): no ripple.
+template <class C>
+HD void fe_mul_wide(uint32_t* T, const Fe<C>& a, const Fe<C>& b) {
+  BN_COUNT_MACS(64);
+  uint32_t E[17], O[17];
+#pragma unroll
+  for (int k = 0; k < 17; k++) E[k] = O[k] = 0;
+  {
+    const uint32_t b0 = b.v[0];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      uint64_t t = (uint64_t)a.v[j] * b0;
+      E[j] = (uint32_t)t;
+      E[j + 1] = (uint32_t)(t >> 32);
+      uint64_t u = (uint64_t)a.v[j + 1] * b0;
+      O[j + 1] = (uint32_t)u;
+      O[j + 2] = (uint32_t)(u >> 32);
+    }
+  }
+#pragma unroll
+  for (int i = 1; i < 8; i++) {
+    const uint32_t bi = b.v[i];
+    const int je = i & 1;        // first j with i + j even
+    const int jo = 1 - (i & 1);  // first j with i + j odd
+#pragma unroll
+    for (int j = je; j < 8; j += 2) {
+      E[i + j] = (j == je) ? cc::mad_lo_cc(a.v[j], bi, E[i + j]) : cc::madc_lo_cc(a.v[j], bi, E[i + j]);
+      E[i + j + 1] = cc::madc_hi_cc(a.v[j], bi, E[i + j + 1]);
+    }
+    E[i + je + 8] = cc::addc(E[i + je + 8], 0u);
+#pragma unroll
+    for (int j = jo; j < 8; j += 2) {
+      O[i + j] = (j == jo) ? cc::mad_lo_cc(a.v[j], bi, O[i + j]) : cc::madc_lo_cc(a.v[j], bi, O[i + j]);
+      O[i + j + 1] = cc::madc_hi_cc(a.v[j], bi, O[i + j + 1]);
+    }
+    O[i + jo + 8] = cc::addc(O[i + jo + 8], 0u);
+  }
+  T[0] = cc::add_cc(E[0], O[0]);
+#pragma unroll
+  for (int k = 1; k < 15; k++) T[k] = cc::addc_cc(E[k], O[k]);
+  T[15] = cc::addc(E[15], O[15]);
+}
+
+// T (16 words, T < m * 2^256) -> T / 2^256 mod m, fully reduced.
+//   REDC(T) = T_hi + (T_lo + Q m) / 2^256,  Q = -T_lo / m mod 2^256
+// The second term is the word-serial reduction of the low half alone (the reduction rows of fe_mul_inl with the
+// accumulator initialised to T_lo); it is <= m, so the sum is < 2m and one conditional subtraction finishes.
+template <class C>
+HD Fe<C> fe_redc_wide(const uint32_t* T) {
+  BN_COUNT_MACS(72);
+  uint32_t W[2][18];
+#pragma unroll
+  for (int k = 0; k < 18; k++) W[0][k] = W[1][k] = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) W[0][k] = T[k];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint32_t* Cw = W[i & 1];
+    uint32_t* Dw = W[(i & 1) ^ 1];
+    if (i > 0) Cw[i] = cc::add_cc(Cw[i], Dw[i]);  // fold; the carry enters the odd chain below
+    const uint32_t q = Cw[i] * C::inv;
+#pragma unroll
+    for (int j = 1; j < 8; j += 2) {
+      Dw[i + j] = (j == 1 && i == 0) ? cc::mad_lo_cc(C::mod(j), q, Dw[i + j]) : cc::madc_lo_cc(C::mod(j), q, Dw[i + j]);
+      Dw[i + j + 1] = cc::madc_hi_cc(C::mod(j), q, Dw[i + j + 1]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      Cw[i + j] = (j == 0) ? cc::mad_lo_cc(C::mod(j), q, Cw[i + j]) : cc::madc_lo_cc(C::mod(j), q, Cw[i + j]);
+      Cw[i + j + 1] = cc::madc_hi_cc(C::mod(j), q, Cw[i + j + 1]);
+    }
+    Cw[i + 8] = cc::addc(Cw[i + 8], 0u);
+  }
+  // U = W[0][8..15] + W[1][8..15] (<= m), r = U + T_hi (< 2m)
+  Fe<C> r;
+  r.v[0] = cc::add_cc(W[0][8], W[1][8]);
+#pragma unroll
+  for (int k = 1; k < 8; k++) r.v[k] = cc::addc_cc(W[0][8 + k], W[1][8 + k]);
+  r.v[0] = cc::add_cc(r.v[0], T[8]);
+#pragma unroll
+  for (int k = 1; k < 8; k++) r.v[k] = cc::addc_cc(r.v[k], T[8 + k]);
+  fe_reduce_once<C>(r.v);
+  return r;
+}
+
+// X -= Y over 16 words; returns the borrow mask (0 or 0xffffffff)
+HD uint32_t wide_sub(uint32_t* X, const uint32_t* Y) {
+  X[0] = cc::sub_cc(X[0], Y[0]);
+#pragma unroll
+  for (int k = 1; k < 16; k++) X[k] = cc::subc_cc(X[k], Y[k]);
+  return cc::subc(0u, 0u);
+}
+// X += (m << 256) & mask   (wraps modulo 2^512: cancels the borrow of a preceding wide_sub)
+template <class C>
+HD void wide_add_mod_hi(uint32_t* X, uint32_t mask) {
+  X[8] = cc::add_cc(X[8], C::mod(0) & mask);
+#pragma unroll
+  for (int k = 1; k < 7; k++) X[8 + k] = cc::addc_cc(X[8 + k], C::mod(k) & mask);
+  X[15] = cc::addc(X[15], C::mod(7) & mask);
+}
 
 template <class C>
 HDN Fe<C> fe_mul(Fe<C> a, Fe<C> b) {
-  BN_COUNT_MUL();
+  BN_COUNT_MACS(136);
   return fe_mul_inl(a, b);
 }
 

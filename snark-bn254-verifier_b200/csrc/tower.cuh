@@ -51,12 +51,23 @@ HD Fp2 conj(const Fp2& a) { return Fp2{a.c0, fe_neg(a.c1)}; }
 HD bool is_zero(const Fp2& a) { return fe_is_zero(a.c0) && fe_is_zero(a.c1); }
 HD bool eq(const Fp2& a, const Fp2& b) { return fe_eq(a.c0, b.c0) && fe_eq(a.c1, b.c1); }
 
-// Karatsuba: 3 base multiplications.  Out of line, operands by value (registers): one copy in the binary.
+// Karatsuba with lazy reduction: 3 full 512-bit products and 2 Montgomery reductions (336 multiply-adds instead of
+// the 408 of three Montgomery multiplications).  Out of line, operands by value (registers): one copy in the binary.
+//   c0 = a0 b0 - a1 b1           (+ p 2^256 when negative: still < p 2^256 and congruent)
+//   c1 = (a0 + a1)(b0 + b1) - a0 b0 - a1 b1      (sums unreduced, < 2p; the difference is a0 b1 + a1 b0 >= 0)
 HDN Fp2 mul(Fp2 a, Fp2 b) {
-  Fp t0 = fe_mul(a.c0, b.c0);
-  Fp t1 = fe_mul(a.c1, b.c1);
-  Fp s = fe_mul(fe_add_nr(a.c0, a.c1), fe_add_nr(b.c0, b.c1));  // operands < 2p: still fully reduced
-  return Fp2{fe_sub(t0, t1), fe_sub(fe_sub(s, t0), t1)};
+  uint32_t T0[16], T1[16], S[16];
+  fe_mul_wide(T0, a.c0, b.c0);
+  fe_mul_wide(T1, a.c1, b.c1);
+  fe_mul_wide(S, fe_add_nr(a.c0, a.c1), fe_add_nr(b.c0, b.c1));
+  wide_sub(S, T0);
+  wide_sub(S, T1);
+  Fp2 r;
+  r.c1 = fe_redc_wide<FpCfg>(S);
+  uint32_t bw = wide_sub(T0, T1);
+  wide_add_mod_hi<FpCfg>(T0, bw);
+  r.c0 = fe_redc_wide<FpCfg>(T0);
+  return r;
 }
 // (a0+a1)(a0-a1), 2 a0 a1
 HDN Fp2 sqr(Fp2 a) {

@@ -143,10 +143,22 @@ int hs_plonk_verify(void* vk, const uint8_t* proof, uint32_t len, const uint8_t*
   PlonkDebug dbg{g1, fr, miller, gt};
   return plonk_verify_one(*(PlonkVkDev*)vk, proof, len, inputs, n_inputs, rnd, dbg);
 }
-unsigned long long hs_mul_count(int reset) {
+void hs_fp2_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {  // 16 words each: c0 | c1 (Montgomery)
+  Fp2 x, y;
+  memcpy(x.c0.v, a, 32), memcpy(x.c1.v, a + 8, 32), memcpy(y.c0.v, b, 32), memcpy(y.c1.v, b + 8, 32);
+  Fp2 z = mul(x, y);
+  memcpy(r, z.c0.v, 32), memcpy(r + 8, z.c1.v, 32);
+}
+void hs_fp2_sqr(uint32_t* r, const uint32_t* a) {
+  Fp2 x;
+  memcpy(x.c0.v, a, 32), memcpy(x.c1.v, a + 8, 32);
+  Fp2 z = sqr(x);
+  memcpy(r, z.c0.v, 32), memcpy(r + 8, z.c1.v, 32);
+}
+unsigned long long hs_mul_count(int reset) {  // limb multiply-adds since the last reset
 #ifdef BN254_COUNT_MULS
-  unsigned long long c = fe_mul_counter();
-  if (reset) fe_mul_counter() = 0;
+  unsigned long long c = fe_mac_counter();
+  if (reset) fe_mac_counter() = 0;
   return c;
 #else
   (void)reset;

@@ -39,6 +39,35 @@ def test_montgomery_mul_both_fields(hs):
             assert _val(out) == a * b * rinv % mod
 
 
+def test_fp2_mul_sqr_lazy_reduction_edge_cases(hs):
+    """The lazy-reduction Fp2 multiplier (3 wide products + 2 wide reductions) on random and extreme operands."""
+    import random
+    rng = random.Random(7)
+    Rm = 1 << 256
+    rinv = pow(Rm, -1, bo.P)
+    edge = [0, 1, 2, bo.P - 1, bo.P - 2, (bo.P - 1) // 2, (1 << 253), Rm % bo.P, (Rm * Rm) % bo.P, 0xFFFFFFFF, (1 << 224) - 1]
+
+    def words(c0, c1):
+        return (ctypes.c_uint32 * 16)(*([(c0 >> (32 * i)) & 0xFFFFFFFF for i in range(8)] +
+                                        [(c1 >> (32 * i)) & 0xFFFFFFFF for i in range(8)]))
+
+    def val(a):
+        return sum(int(a[i]) << (32 * i) for i in range(8)), sum(int(a[8 + i]) << (32 * i) for i in range(8))
+
+    cases = [(a0, a1, b0, b1) for a0 in edge[:6] for a1 in edge[:6] for b0 in (0, bo.P - 1, 5) for b1 in (0, bo.P - 1, 7)]
+    cases += [tuple(rng.choice(edge) for _ in range(4)) for _ in range(300)]
+    cases += [tuple(rng.randrange(bo.P) for _ in range(4)) for _ in range(1500)]
+    out = (ctypes.c_uint32 * 16)()
+    for a0, a1, b0, b1 in cases:
+        hs.hs_fp2_mul(out, words(a0, a1), words(b0, b1))
+        # Montgomery: inputs are xR, result is (x y) R  => result = a b R^-1
+        c0 = (a0 * b0 - a1 * b1) * rinv % bo.P
+        c1 = (a0 * b1 + a1 * b0) * rinv % bo.P
+        assert val(out) == (c0, c1), (a0, a1, b0, b1)
+        hs.hs_fp2_sqr(out, words(a0, a1))
+        assert val(out) == ((a0 * a0 - a1 * a1) * rinv % bo.P, 2 * a0 * a1 * rinv % bo.P)
+
+
 def test_pairing_products_match_golden(hs):
     for c in load_json("pairing_golden.json"):
         ml, gt = ctypes.create_string_buffer(384), ctypes.create_string_buffer(384)

@@ -27,8 +27,9 @@ def main(write=True):
     hs.hs_plonk_vk_new.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
     hs.hs_plonk_verify.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_int,
                                    ctypes.c_char_p] + [ctypes.c_char_p] * 4
-    out = {"macs_per_mul": 136, "unit": "field multiplications per proof (Fp and Fr), counted on the host build of the "
-                                        "kernels' per-proof routines"}
+    out = {"macs_per_mul": 136, "unit": "limb multiply-adds (32x32+64) per proof, counted on the host build of the kernels' "
+                                        "per-proof routines: 136 per Montgomery multiplication, 64 per wide product, "
+                                        "72 per wide reduction; *_fp_mul = macs / 136 (multiplication equivalents)"}
     # Groth16: mean over 8 trapdoor proofs (valid and corrupted cost the same)
     case = load_json("groth16_golden.json")["cases"][0]
     vk = bo.load_groth16_verifying_key_from_bytes(bytes.fromhex(case["vk"]))
@@ -41,14 +42,15 @@ def main(write=True):
         inputs = b"".join(int(x).to_bytes(32, "big") for x in pr["inputs"])
         hs.hs_groth16_verify(h, bytes.fromhex(pr["proof"]), 256, inputs, 2, None, None, None)
         n += 1
-    out["groth16_fp_mul"] = hs.hs_mul_count(1) // n
+    out["groth16_macs"] = hs.hs_mul_count(1) // n
+    out["groth16_fp_mul"] = out["groth16_macs"] // 136
     # raw pairing products
     for c in load_json("pairing_golden.json"):
         if c["is_one"]:
             continue
         hs.hs_mul_count(1)
         hs.hs_pairing_product(c["k"], bytes.fromhex(c["g1"]), bytes.fromhex(c["g2"]), None, None)
-        out["pairing_product_k%d_fp_mul" % c["k"]] = hs.hs_mul_count(1)
+        out["pairing_product_k%d_macs" % c["k"]] = hs.hs_mul_count(1)
     # PlonK: full path (valid proof) and early reject
     vkb = plonk_vk_bytes()
     pv = hs.hs_plonk_vk_new(vkb, len(vkb))
@@ -56,10 +58,11 @@ def main(write=True):
     inputs = b"".join(x.to_bytes(32, "big") for x in xs)
     hs.hs_mul_count(1)
     assert hs.hs_plonk_verify(pv, pr, len(pr), inputs, 2, (77).to_bytes(32, "big"), None, None, None, None) == 0
-    out["plonk_full_path_mul"] = hs.hs_mul_count(1)
+    out["plonk_full_path_macs"] = hs.hs_mul_count(1)
+    out["plonk_full_path_mul"] = out["plonk_full_path_macs"] // 136
     bad = [m for m in load_json("plonk_mutations.json") if m["program"] == "fibonacci" and m["mutation"] == "claimed0+1"][0]
     hs.hs_plonk_verify(pv, bytes.fromhex(bad["raw_proof"]), 904, inputs, 2, (77).to_bytes(32, "big"), None, None, None, None)
-    out["plonk_early_reject_mul"] = hs.hs_mul_count(1)
+    out["plonk_early_reject_mul"] = hs.hs_mul_count(1) // 136
     if write:
         json.dump(out, open(os.path.join(ROOT, "profiles", "workcount.json"), "w"), indent=1)
     return out
