@@ -38,7 +38,7 @@ MACS_PER_FPMUL = 136
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1 << 16, help="proofs per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -60,7 +60,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -91,6 +91,16 @@ class ClockSampler:
         pw = [float(r[3]) for r in self.rows if len(r) >= 8 and r[3].replace(".", "").isdigit()]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def ncu_traffic(n):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        t = json.load(open(p))["k_groth16_verify"]
+        return t["dram_bytes_per_launch"] if t["batch"] == n else None
+    except Exception:
+        return None
 
 
 def work_per_proof():
@@ -295,7 +305,7 @@ def run_b200(args):
     achieved = macs_per_proof * n * args.steps / (sum(kernel_ms) * 1e-3)  # this rank's kernel
     roofline = {
         "bound": "int32-imad", "achieved": achieved / 1e12, "peak": peak["wide_mac_per_s"] / 1e12, "unit": "TMAC/s",
-        "frac": achieved / peak["wide_mac_per_s"], "traffic": None,
+        "frac": achieved / peak["wide_mac_per_s"], "traffic": ncu_traffic(n),
         "kernel": "k_groth16_verify", "macs_per_proof": macs_per_proof, "fp_mul_per_proof": work["groth16_fp_mul"],
         "peak_source": "measured live: bn254v_imad_peak (independent IMAD.WIDE.U32 accumulate chains, 8 warps/SMSP, "
                        "all SMs); MEASURED_PEAKS.json holds no integer peak",
