@@ -16,6 +16,7 @@
 #include "gnark_host.h"
 #include "groth16.cuh"
 #include "plonk.cuh"
+#include "lanepair.cuh"
 #include "synth.cuh"
 
 using namespace bn254;
@@ -181,6 +182,36 @@ __global__ void k_plonk_vk_prepare(PlonkVkDev* vk) {
   if (blockIdx.x == 0 && threadIdx.x == 0) plonk_vk_prepare(*vk);
 }
 
+// ---- lane-pair kernels (lanepair.cuh): two adjacent lanes per proof; no early return (phase barriers inside)
+template <int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB)
+    k_groth16_verify_lp(const Groth16VkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride,
+                        const uint32_t* __restrict__ proof_len, const uint8_t* __restrict__ inputs, int n_inputs,
+                        size_t n, uint8_t* __restrict__ status, uint8_t* dbg_l, uint8_t* dbg_m, uint8_t* dbg_gt) {
+  size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+  const bool live = i < n;
+  if (!live) i = n - 1;  // spare pairs of the last block redo the last proof and write nothing
+  Groth16Debug dbg{live && dbg_l ? dbg_l + 64 * i : nullptr, live && dbg_m ? dbg_m + 384 * i : nullptr,
+                   live && dbg_gt ? dbg_gt + 384 * i : nullptr};
+  uint32_t len = proof_len ? proof_len[i] : (uint32_t)stride;
+  if (len > stride) len = (uint32_t)stride;
+  int st = lp::groth16_verify_pair(*vk, proofs + stride * i, len, inputs + (size_t)32 * n_inputs * i, n_inputs, dbg);
+  if (live && !(threadIdx.x & 1)) status[i] = (uint8_t)st;
+}
+
+template <int KP, int TPB>
+__global__ void __launch_bounds__(TPB, 1)
+    k_pairing_product_lp(const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2, size_t n,
+                         uint8_t* __restrict__ is_one, uint8_t* miller_out, uint8_t* gt_out) {
+  size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+  const bool live = i < n;
+  if (!live) i = n - 1;
+  bool one = lp::pairing_product_pair<KP>(g1 + (size_t)64 * KP * i, g2 + (size_t)128 * KP * i,
+                                          live && miller_out ? miller_out + 384 * i : nullptr,
+                                          live && gt_out ? gt_out + 384 * i : nullptr);
+  if (live && !(threadIdx.x & 1)) is_one[i] = one ? 1 : 0;
+}
+
 // ---- PlonK, staged (plonk.cuh): A (per proof) -> terms 0 (per proof x term) -> C (per survivor) -> terms 1 -> E.
 // `list` holds the indices of the proofs that are still alive after stage A (early rejects cost nothing further);
 // a slot is set to -1 when a later stage ends the proof.
@@ -230,7 +261,7 @@ __global__ void __launch_bounds__(64)
   int st = plonk_stage_c(work[i], *vk, proofs + stride * (size_t)i, rnd + (size_t)32 * i, plonk_dbg(dp, i));
   if (st != BN254V_OK_TRUE) {
     status[i] = (uint8_t)st;
-    list[slot] = -1;
+    list[slot] = -(i + 1);  // dead: later stages skip it (the lane-pair stage E recomputes on it and writes nothing)
   }
 }
 
@@ -244,6 +275,26 @@ __global__ void __launch_bounds__(TPB, 1)
   int i = list[slot];
   if (i < 0) return;
   status[i] = (uint8_t)plonk_stage_e(work[i], *vk, proofs + stride * (size_t)i, plonk_dbg(dp, i));
+}
+
+template <int TPB>
+__global__ void __launch_bounds__(TPB, 1)
+    k_plonk_stage_e_lp(const PlonkVkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride,
+                       uint8_t* __restrict__ status, PlonkWork* work, const int* __restrict__ list,
+                       const int* __restrict__ count, PlonkDbgPtrs dp) {
+  const int cnt = *count;
+  if (cnt == 0) return;  // uniform over the grid
+  int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+  bool live = slot < cnt;
+  if (!live) slot = cnt - 1;
+  int i = list[slot];
+  if (i < 0) {  // ended in stage C: recompute on its (well-formed) data, write nothing
+    live = false;
+    i = -(i + 1);
+  }
+  PlonkDebug dbg = live ? plonk_dbg(dp, i) : PlonkDebug{nullptr, nullptr, nullptr, nullptr};
+  int st = lp::plonk_stage_e_pair(work[i], *vk, proofs + stride * (size_t)i, dbg);
+  if (live && !(threadIdx.x & 1)) status[i] = (uint8_t)st;
 }
 
 template <int KP, int TPB>
@@ -278,7 +329,8 @@ __global__ void __launch_bounds__(BN_TPB)
 // Launch shapes.  One proof per thread; the block is the unit that the phase barriers keep in step, and the grid should
 // cover the SMs evenly.  `pick_shape`: big batches use 448-thread blocks, one per SM (14 warps, 128 registers/thread;
 // 2^16 proofs = 147 blocks on 148 SMs); small batches use smaller blocks so that every SM gets work.
-// BN254V_VARIANT overrides the choice for experiments (1: 128x2, 2: 128x4, 3: 448x1, 4: 512x1, 5: 256x2, 6: 32x1).
+// BN254V_VARIANT overrides the choice for experiments (1: 128x2, 2: 128x4, 3: 448x1, 6: 32x1; 20/21/24: the
+// lane-pair kernels at 448x1 / 448x2 / 512x1 -- measured equal or slower than one proof per thread).
 static int g_sm_count = 148;
 static int pick_shape(size_t m) {
   static int forced = -2;
@@ -298,11 +350,19 @@ static void launch_groth16_verify(cudaStream_t st, const Groth16VkDev* vk, const
 #define LV(TPB, MINB)                                                                                              \
   k_groth16_verify<TPB, MINB><<<(unsigned)((m + TPB - 1) / TPB), TPB, 0, st>>>(vk, proofs, stride, lens, inputs, \
                                                                                n_inputs, m, status, l, ml, gt)
+#define LVP(TPB, MINB)                                                                                  \
+  k_groth16_verify_lp<TPB, MINB><<<(unsigned)((2 * m + TPB - 1) / TPB), TPB, 0, st>>>(                    \
+      vk, proofs, stride, lens, inputs, n_inputs, m, status, l, ml, gt)
+  switch (pick_shape(m)) {
+    case 20: LVP(448, 1); return;  // experimental lane-pair kernels (lanepair.cuh): two lanes per proof
+    case 21: LVP(448, 2); return;
+    case 24: LVP(512, 1); return;
+    default: break;
+  }
+#undef LVP
   switch (pick_shape(m)) {
     case 2: LV(128, 4); break;
     case 3: LV(448, 1); break;
-    case 4: LV(512, 1); break;
-    case 5: LV(256, 2); break;
     case 6: LV(32, 1); break;
     default: LV(128, 2); break;
   }
@@ -694,7 +754,10 @@ int bn254v_plonk_verify_batch(const bn254v_vk* vk, const uint8_t* proofs, size_t
                                                     work.as<PlonkWork>(), list.as<int>(), count.as<int>(), dp);
         k_plonk_terms<<<dim3(g64, n_terms), 64, 0, dev.stream>>>(dvk, cp, proof_stride, work.as<PlonkWork>(),
                                                                  list.as<int>(), count.as<int>(), 1);
-        if (pick_shape(cm) == 6)
+        if (pick_shape(cm) >= 20)
+          k_plonk_stage_e_lp<128><<<(unsigned)((2 * cm + 127) / 128), 128, 0, dev.stream>>>(
+              dvk, cp, proof_stride, cst, work.as<PlonkWork>(), list.as<int>(), count.as<int>(), dp);
+        else if (pick_shape(cm) == 6)
           k_plonk_stage_e<32><<<(unsigned)((cm + 31) / 32), 32, 0, dev.stream>>>(dvk, cp, proof_stride, cst,
                                                                                  work.as<PlonkWork>(), list.as<int>(),
                                                                                  count.as<int>(), dp);
@@ -751,6 +814,10 @@ int bn254v_pairing_product_batch(const uint8_t* g1, const uint8_t* g2, int k, si
       p.g1.as<uint8_t>(), p.g2.as<uint8_t>(), m, p.one.as<uint8_t>(), p.m.as<uint8_t>(), p.gt.as<uint8_t>())
 #define LAUNCH_PP(KP)                          \
   switch (pick_shape(m)) {                     \
+    case 20: case 21: case 24:                                                                                    \
+      k_pairing_product_lp<KP, 448><<<(unsigned)((2 * m + 447) / 448), 448, 0, dev.stream>>>(                     \
+          p.g1.as<uint8_t>(), p.g2.as<uint8_t>(), m, p.one.as<uint8_t>(), p.m.as<uint8_t>(), p.gt.as<uint8_t>()); \
+      break;                                   \
     case 3: case 4: LAUNCH_PP2(KP, 448); break; \
     case 6: LAUNCH_PP2(KP, 32); break;         \
     default: LAUNCH_PP2(KP, 128); break;       \

@@ -100,186 +100,7 @@ HD Fp2 fp2_b2() {
   return r;
 }
 
-// ------------------------------------------------------------------------------------------ Fp6
-// Fp6 / Fp12 values live in (local) memory; every operation below is destination-passing -- `r` may alias any
-// input -- so no 192 / 384-byte temporaries are created for return values and the per-thread stack stays small.
-struct Fp6 {
-  Fp2 c0, c1, c2;
-};
-HD Fp6 fp6_zero() { return Fp6{fp2_zero(), fp2_zero(), fp2_zero()}; }
-HD Fp6 fp6_one() { return Fp6{fp2_one(), fp2_zero(), fp2_zero()}; }
-HD bool eq(const Fp6& a, const Fp6& b) { return eq(a.c0, b.c0) && eq(a.c1, b.c1) && eq(a.c2, b.c2); }
-
-// element-wise helpers over n consecutive Fp (an Fp6 is 6, an Fp12 is 12): rolled loops, one copy in the binary
-HDN void fpn_add(Fp* r, const Fp* a, const Fp* b, int n) {
-#pragma unroll 1
-  for (int i = 0; i < n; i++) r[i] = fe_add(a[i], b[i]);
-}
-HDN void fpn_sub(Fp* r, const Fp* a, const Fp* b, int n) {
-#pragma unroll 1
-  for (int i = 0; i < n; i++) r[i] = fe_sub(a[i], b[i]);
-}
-HDN void fpn_neg(Fp* r, const Fp* a, int n) {
-#pragma unroll 1
-  for (int i = 0; i < n; i++) r[i] = fe_neg(a[i]);
-}
-HD void add(Fp6& r, const Fp6& a, const Fp6& b) { fpn_add(&r.c0.c0, &a.c0.c0, &b.c0.c0, 6); }
-HD void sub(Fp6& r, const Fp6& a, const Fp6& b) { fpn_sub(&r.c0.c0, &a.c0.c0, &b.c0.c0, 6); }
-HD void neg(Fp6& r, const Fp6& a) { fpn_neg(&r.c0.c0, &a.c0.c0, 6); }
-HD void dbl(Fp6& r, const Fp6& a) { fpn_add(&r.c0.c0, &a.c0.c0, &a.c0.c0, 6); }
-// multiply by v
-HD void mul_v(Fp6& r, const Fp6& a) {
-  Fp2 t = mul_xi(a.c2);
-  Fp2 a0 = a.c0, a1 = a.c1;
-  r.c0 = t;
-  r.c1 = a0;
-  r.c2 = a1;
-}
-
-// Karatsuba: 6 Fp2 multiplications
-HDN void mul(Fp6& r, const Fp6& a, const Fp6& b) {
-  Fp2 v0 = mul(a.c0, b.c0);
-  Fp2 v1 = mul(a.c1, b.c1);
-  Fp2 v2 = mul(a.c2, b.c2);
-  Fp2 t0 = sub(sub(mul(add(a.c1, a.c2), add(b.c1, b.c2)), v1), v2);
-  Fp2 t1 = sub(sub(mul(add(a.c0, a.c1), add(b.c0, b.c1)), v0), v1);
-  Fp2 t2 = sub(sub(mul(add(a.c0, a.c2), add(b.c0, b.c2)), v0), v2);
-  r.c0 = add(v0, mul_xi(t0));
-  r.c1 = add(t1, mul_xi(v2));
-  r.c2 = add(t2, v1);
-}
-// CH-SQR2: 2 mul + 3 sqr in Fp2
-HDN void sqr(Fp6& r, const Fp6& a) {
-  Fp2 s0 = sqr(a.c0);
-  Fp2 s1 = dbl(mul(a.c0, a.c1));
-  Fp2 s2 = sqr(add(sub(a.c0, a.c1), a.c2));
-  Fp2 s3 = dbl(mul(a.c1, a.c2));
-  Fp2 s4 = sqr(a.c2);
-  r.c0 = add(s0, mul_xi(s3));
-  r.c1 = add(s1, mul_xi(s4));
-  r.c2 = sub(add(add(s1, s2), s3), add(s0, s4));
-}
-HDN void inv(Fp6& r, const Fp6& a) {
-  Fp2 c0 = sub(sqr(a.c0), mul_xi(mul(a.c1, a.c2)));
-  Fp2 c1 = sub(mul_xi(sqr(a.c2)), mul(a.c0, a.c1));
-  Fp2 c2 = sub(sqr(a.c1), mul(a.c0, a.c2));
-  Fp2 t = add(mul(a.c0, c0), mul_xi(add(mul(a.c2, c1), mul(a.c1, c2))));
-  Fp2 ti = inv(t);
-  r.c0 = mul(c0, ti);
-  r.c1 = mul(c1, ti);
-  r.c2 = mul(c2, ti);
-}
-
-// ------------------------------------------------------------------------------------------ Fp12
-struct Fp12 {
-  Fp6 c0, c1;
-};
-HD Fp12 fp12_one() { return Fp12{fp6_one(), fp6_zero()}; }
-HD bool eq(const Fp12& a, const Fp12& b) { return eq(a.c0, b.c0) && eq(a.c1, b.c1); }
-// unitary inverse (conjugate)
-HD void conj(Fp12& r, const Fp12& a) {
-  if (&r != &a) r.c0 = a.c0;
-  neg(r.c1, a.c1);
-}
-
-// Karatsuba: 3 Fp6 multiplications
-HDN void mul(Fp12& r, const Fp12& a, const Fp12& b) {
-  Fp6 v0, v1, s, t;
-  mul(v0, a.c0, b.c0);
-  mul(v1, a.c1, b.c1);
-  add(s, a.c0, a.c1);
-  add(t, b.c0, b.c1);
-  mul(s, s, t);
-  sub(s, s, v0);
-  sub(r.c1, s, v1);
-  mul_v(t, v1);
-  add(r.c0, v0, t);
-}
-// complex squaring: 2 Fp6 multiplications
-HDN void sqr(Fp12& r, const Fp12& a) {
-  Fp6 ab, s, t;
-  mul(ab, a.c0, a.c1);
-  add(s, a.c0, a.c1);
-  mul_v(t, a.c1);
-  add(t, t, a.c0);
-  mul(s, s, t);       // (a0 + a1)(a0 + v a1)
-  sub(s, s, ab);
-  mul_v(t, ab);
-  sub(r.c0, s, t);
-  dbl(r.c1, ab);
-}
-HDN void inv(Fp12& r, const Fp12& a) {
-  Fp6 t, u;
-  sqr(t, a.c0);
-  sqr(u, a.c1);
-  mul_v(u, u);
-  sub(t, t, u);
-  inv(t, t);
-  mul(r.c0, a.c0, t);
-  mul(u, a.c1, t);
-  neg(r.c1, u);
-}
-
-// f <- f * (x0 + x2 v^2 + x4 v w)  -- substrate-bn's mul_by_024(ell_0 = x0, ell_vw = x4, ell_vv = x2):
-// the sparse operand is Fq12{c0: (x0, 0, x2), c1: (0, x4, 0)}.  14 Fp2 multiplications.
-HDN void mul_by_024(Fp12& f, const Fp2& x0, const Fp2& x4, const Fp2& x2) {
-  Fp6 AS0, BS1, T, S;
-  {
-    const Fp6& A = f.c0;
-    // A * (x0, 0, x2): 5 mul
-    Fp2 a0x0 = mul(A.c0, x0);
-    Fp2 a2x2 = mul(A.c2, x2);
-    Fp2 a1x0 = mul(A.c1, x0);
-    Fp2 a1x2 = mul(A.c1, x2);
-    Fp2 cross = sub(sub(mul(add(A.c0, A.c2), add(x0, x2)), a0x0), a2x2);  // a0x2 + a2x0
-    AS0.c0 = add(a0x0, mul_xi(a1x2));
-    AS0.c1 = add(a1x0, mul_xi(a2x2));
-    AS0.c2 = cross;
-  }
-  {
-    const Fp6& B = f.c1;
-    // B * (0, x4, 0): 3 mul -> (xi b2x4, b0x4, b1x4)
-    BS1.c0 = mul_xi(mul(B.c2, x4));
-    BS1.c1 = mul(B.c0, x4);
-    BS1.c2 = mul(B.c1, x4);
-  }
-  // (A+B) * (x0, x4, x2): 6 mul
-  S.c0 = x0, S.c1 = x4, S.c2 = x2;
-  add(T, f.c0, f.c1);
-  mul(T, T, S);
-  sub(T, T, AS0);
-  sub(f.c1, T, BS1);
-  mul_v(BS1, BS1);
-  add(f.c0, AS0, BS1);
-}
-
-// Granger-Scott squaring for cyclotomic-subgroup elements: 6 Fp2 mul-equivalents (18 m).
-HD void fp4_sqr(Fp2& t0, Fp2& t1, const Fp2& z0, const Fp2& z1) {
-  Fp2 tmp = mul(z0, z1);
-  t0 = sub(sub(mul(add(z0, z1), add(z0, mul_xi(z1))), tmp), mul_xi(tmp));
-  t1 = dbl(tmp);
-}
-HDN void cyclotomic_sqr(Fp12& r, const Fp12& a) {
-  // z0=c0.c0 z4=c0.c1 z3=c0.c2 z2=c1.c0 z1=c1.c1 z5=c1.c2; each output pair depends on one input pair only
-  Fp2 t0, t1;
-  {
-    Fp2 z0 = a.c0.c0, z1 = a.c1.c1;
-    fp4_sqr(t0, t1, z0, z1);
-    r.c0.c0 = add(dbl(sub(t0, z0)), t0);  // 3 t0 - 2 z0
-    r.c1.c1 = add(dbl(add(t1, z1)), t1);  // 3 t1 + 2 z1
-  }
-  Fp2 z2 = a.c1.c0, z3 = a.c0.c2, z4 = a.c0.c1, z5 = a.c1.c2;
-  Fp2 t2, t3;
-  fp4_sqr(t2, t3, z2, z3);
-  fp4_sqr(t0, t1, z4, z5);  // t4, t5
-  Fp2 tmp = mul_xi(t1);
-  r.c1.c0 = add(dbl(add(tmp, z2)), tmp);
-  r.c0.c2 = add(dbl(sub(t0, z3)), t0);
-  r.c0.c1 = add(dbl(sub(t2, z4)), t2);
-  r.c1.c2 = add(dbl(add(t3, z5)), t3);
-}
-
-// Frobenius^k, k in {1,2,3}: coefficient a_i of w^i -> conj^k(a_i) * xi^(i(p^k-1)/6)
+// Frobenius coefficients xi^(i(p^k-1)/6)
 template <int KK>
 HD Fp2 frob_coeff(int i) {  // i = 1..5
   Fp2 r;
@@ -289,25 +110,9 @@ HD Fp2 frob_coeff(int i) {  // i = 1..5
   return r;
 }
 template <int KK>
-HDN void frobenius(Fp12& r, const Fp12& a) {
-  // w-power order: a0=c0.c0, a1=c1.c0, a2=c0.c1, a3=c1.c1, a4=c0.c2, a5=c1.c2 (element-wise: r may alias a)
-  if (KK & 1) {
-    r.c0.c0 = conj(a.c0.c0);
-    r.c1.c0 = mul(conj(a.c1.c0), frob_coeff<KK>(1));
-    r.c0.c1 = mul(conj(a.c0.c1), frob_coeff<KK>(2));
-    r.c1.c1 = mul(conj(a.c1.c1), frob_coeff<KK>(3));
-    r.c0.c2 = mul(conj(a.c0.c2), frob_coeff<KK>(4));
-    r.c1.c2 = mul(conj(a.c1.c2), frob_coeff<KK>(5));
-  } else {
-    // p^2: coefficients lie in Fp (c1 == 0)
-    r.c0.c0 = a.c0.c0;
-    r.c1.c0 = scale(a.c1.c0, frob_coeff<KK>(1).c0);
-    r.c0.c1 = scale(a.c0.c1, frob_coeff<KK>(2).c0);
-    r.c1.c1 = scale(a.c1.c1, frob_coeff<KK>(3).c0);
-    r.c0.c2 = scale(a.c0.c2, frob_coeff<KK>(4).c0);
-    r.c1.c2 = scale(a.c1.c2, frob_coeff<KK>(5).c0);
-  }
-}
+HD Fp frob_coeff_fp(int i) { return frob_coeff<KK>(i).c0; }
+
+#include "tower_body.inc"
 
 // canonical serialisation: 12 x 32-byte BE, order c0.c0.c0, c0.c0.c1, c0.c1.c0, ..., c1.c2.c1
 HDN void fp12_to_bytes(uint8_t* out, const Fp12& a) {
