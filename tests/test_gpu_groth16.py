@@ -159,3 +159,18 @@ print("LANEPAIR-OK")
     env = dict(os.environ, BN254V_VARIANT="20")
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=280)
     assert "LANEPAIR-OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_full_size_sample_against_cpp_oracle(gpu):
+    """2^16 batch: L, Miller and GT of a 2^10 strided sample bit-exact against the C++ restatement of the reference
+    (which recomputes everything per call the way the crate does), and its verdicts on the same sample."""
+    import os
+    import ref_cpu
+    n = 1 << 16
+    vk, proofs, inputs, expected = gpu.groth16_synth(4242, n)
+    idx = np.arange(0, n, n >> 10)
+    status, dbg = gpu.Groth16Verifier.verify_batch(proofs[idx], vk, inputs[idx], debug=True)
+    _, st_c, l_c, ml_c, gt_c = ref_cpu.groth16_verify_batch(vk, proofs[idx], inputs[idx], threads=os.cpu_count() or 1,
+                                                            debug=True)
+    assert (status == st_c).all() and (status == expected[idx]).all()
+    assert (dbg.g1[:, 0] == l_c).all() and (dbg.miller == ml_c).all() and (dbg.gt == gt_c).all()

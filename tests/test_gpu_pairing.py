@@ -43,3 +43,18 @@ def test_pairing_batch_large_properties(gpu):
     _, _, gt_a = gpu.pairing_product_batch(g1[sub], g2[sub], 4, want_values=True)
     _, _, gt_b = gpu.pairing_product_batch(g1[sub][:, ::-1], g2[sub][:, ::-1], 4, want_values=True)
     assert (gt_a == gt_b).all()
+
+
+def test_full_size_config4_against_cpp_oracle(gpu):
+    """BASELINE configs[3] at full size: 2^20 random 4-pair sets, every is_one bit as constructed (odd indices solved
+    to 1); canonical Miller and GT values of a 2^12 strided sample bit-exact against the C++ oracle."""
+    import os
+    import ref_cpu
+    n = 1 << 20
+    g1, g2, expected = gpu.pairing_synth(2025, n, k=4)
+    is_one = gpu.pairing_product_batch(g1, g2, 4)
+    assert (is_one == expected).all() and int(is_one.sum()) == n // 2
+    idx = np.arange(0, n, n >> 12)
+    _, ml, gt = gpu.pairing_product_batch(g1[idx], g2[idx], 4, want_values=True)
+    _, one_c, ml_c, gt_c = ref_cpu.pairing_product_batch(g1[idx], g2[idx], 4, threads=os.cpu_count() or 1)
+    assert (ml == ml_c).all() and (gt == gt_c).all() and (one_c == expected[idx]).all()
