@@ -201,6 +201,17 @@ def secondary_workloads(pkg, work):
     dt = time.perf_counter() - t0
     assert (st == eb).all()
     out["plonk"]["e2e_proofs_per_sec_2e17_batch"] = n * big / dt
+    try:  # CPU side by side: the oracle's C++ restatement of PlonkVerifier::verify on the same records
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ref_cpu
+        cores = host_cores()
+        sample = min(n, max(64 * cores, 256))
+        dtc, stc = ref_cpu.plonk_verify_batch(vk, proofs[:sample], inputs[:sample], rnd[:sample], threads=cores)
+        assert (stc == expected[:sample]).all(), "CPU PlonK oracle disagrees"
+        out["plonk"]["cpu_baseline"] = {"value": sample / dtc, "unit": "proofs/s", "cores": cores, "kind": "port",
+                                        "sample": "first %d records of the same batch, one pass, %.1f s" % (sample, dtc)}
+    except Exception as e:
+        out["plonk"]["cpu_baseline"] = {"value": None, "sample": "unavailable: %r" % (e,)}
     m = 1 << 17
     g1, g2, exp1 = pkg.pairing_synth(11, m, k=4)
     pkg.pairing_product_batch(g1[:1024], g2[:1024], 4)

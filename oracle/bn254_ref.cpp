@@ -22,6 +22,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <utility>
 #include <thread>
 #include <vector>
 
@@ -831,6 +832,352 @@ static void g2_mul_gen(G2A& out, const Fr& k) {
   to_affine(out, scalar_mul(G2A{KC.g2x, KC.g2y}, p));
 }
 
+// ------------------------------------------------------------------------------------------ PlonK (reference shape)
+// verify_plonk and its helpers restated per call, as the crate does it (verifier/src/plonk/verify.rs:46-396,
+// verifier/src/plonk/kzg.rs:46-190, verifier/src/transcript.rs:68-107, verifier/src/hash_to_field.rs:30-97,
+// verifier/src/plonk/converter.rs:18-178): VK decompressed on every call, naive AffineG1::msm (one 256-bit
+// double-and-add per term), generic Fr::pow, three separate Fr inversions, a 2-pair pairing_batch with both G2
+// precomputations.  Statuses as include/bn254v.h.
+enum {
+  ST_ERR_BSB22 = 3, ST_ERR_WITNESS = 4, ST_ERR_INVERSE = 5, ST_ERR_OPENING = 6, ST_ERR_NDIGESTS = 7, ST_ERR_PAIRING = 8,
+  ST_PANIC_DIV0 = 21, ST_PANIC_INDEX = 22
+};
+
+struct Sha256 {
+  uint32_t h[8];
+  uint8_t buf[64];
+  u64 len;
+};
+static inline uint32_t rotr32(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+static void sha_compress(uint32_t* h, const uint8_t* b) {
+  static const uint32_t K[64] = {
+      0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01,
+      0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc,
+      0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147,
+      0x06ca6351, 0x14292967, 0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+      0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08,
+      0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208,
+      0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+  uint32_t w[64];
+  for (int i = 0; i < 16; i++) w[i] = ((uint32_t)b[4 * i] << 24) | (b[4 * i + 1] << 16) | (b[4 * i + 2] << 8) | b[4 * i + 3];
+  for (int i = 16; i < 64; i++) {
+    uint32_t s0 = rotr32(w[i - 15], 7) ^ rotr32(w[i - 15], 18) ^ (w[i - 15] >> 3);
+    uint32_t s1 = rotr32(w[i - 2], 17) ^ rotr32(w[i - 2], 19) ^ (w[i - 2] >> 10);
+    w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+  }
+  uint32_t a = h[0], bb = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+  for (int i = 0; i < 64; i++) {
+    uint32_t t1 = hh + (rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25)) + ((e & f) ^ (~e & g)) + K[i] + w[i];
+    uint32_t t2 = (rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22)) + ((a & bb) ^ (a & c) ^ (bb & c));
+    hh = g, g = f, f = e, e = d + t1, d = c, c = bb, bb = a, a = t1 + t2;
+  }
+  h[0] += a, h[1] += bb, h[2] += c, h[3] += d, h[4] += e, h[5] += f, h[6] += g, h[7] += hh;
+}
+static void sha_init(Sha256& s) {
+  static const uint32_t iv[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+  memcpy(s.h, iv, 32);
+  s.len = 0;
+}
+static void sha_update(Sha256& s, const void* data, size_t n) {
+  const uint8_t* p = (const uint8_t*)data;
+  for (size_t i = 0; i < n; i++) {
+    s.buf[s.len++ & 63] = p[i];
+    if ((s.len & 63) == 0) sha_compress(s.h, s.buf);
+  }
+}
+static void sha_final(Sha256& s, uint8_t* out) {
+  u64 bits = s.len * 8;
+  uint8_t pad = 0x80;
+  sha_update(s, &pad, 1);
+  pad = 0;
+  while ((s.len & 63) != 56) sha_update(s, &pad, 1);
+  uint8_t lb[8];
+  for (int i = 0; i < 8; i++) lb[i] = (uint8_t)(bits >> (56 - 8 * i));
+  sha_update(s, lb, 8);
+  for (int i = 0; i < 8; i++) {
+    out[4 * i] = s.h[i] >> 24, out[4 * i + 1] = s.h[i] >> 16, out[4 * i + 2] = s.h[i] >> 8, out[4 * i + 3] = s.h[i];
+  }
+}
+
+static Fr fr_zero() { return Fr{{0, 0, 0, 0}}; }
+static Fr fr_one() {
+  Fr r;
+  memcpy(r.v, MR.r1, 32);
+  return r;
+}
+static bool fr_is_zero(const Fr& a) { return (a.v[0] | a.v[1] | a.v[2] | a.v[3]) == 0; }
+static bool fr_eq(const Fr& a, const Fr& b) { return memcmp(a.v, b.v, 32) == 0; }
+static Fr fr_neg(const Fr& a) { return fr_sub(fr_zero(), a); }
+static bool fr_from_be(Fr& out, const uint8_t* b) {  // Fr::from_slice: must be < r
+  u64 t[4];
+  bool ok = limbs_from_be(t, b, MR);
+  out = fr_from_plain(t);
+  return ok;
+}
+static Fr fr_from_be_mod_order(const uint8_t* b) {  // Fr::from_bytes_be_mod_order
+  u64 t[4];
+  limbs_from_be(t, b, MR);
+  while (geq(t, MR.m)) sub_n(t, t, MR.m);
+  return fr_from_plain(t);
+}
+static void fr_to_be(uint8_t* b, const Fr& a) {
+  u64 t[4];
+  fr_to_plain(t, a);
+  limbs_to_be(b, t);
+}
+static Fr fr_pow_fr(const Fr& a, const Fr& e_mont) {  // Fr::pow(Fr): generic 256-bit square-and-multiply
+  u64 e[4];
+  fr_to_plain(e, e_mont);
+  Fr r = fr_one();
+  for (int i = 255; i >= 0; i--) {
+    r = fr_mul(r, r);
+    if ((e[i >> 6] >> (i & 63)) & 1) r = fr_mul(r, a);
+  }
+  return r;
+}
+static Fr fr_from_u64(u64 x) {
+  u64 t[4] = {x, 0, 0, 0};
+  return fr_from_plain(t);
+}
+
+struct PlonkVk {
+  u64 size, nb_public;
+  Fr size_inv, generator, coset_shift;
+  G1A s[3], ql, qr, qm, qo, qk, g1;
+  std::vector<G1A> qcp;
+  G2A g2[2];
+  std::vector<u64> cci;
+};
+static u64 be64(const uint8_t* b) { return ((u64)be32(b) << 32) | be32(b + 4); }
+static int parse_plonk_vk(PlonkVk& vk, const uint8_t* buf, size_t len) {  // plonk/converter.rs:18-119
+  if (len < 372) return -1;
+  vk.size = be64(buf);
+  if (!fr_from_be(vk.size_inv, buf + 8) || !fr_from_be(vk.generator, buf + 40)) return -1;
+  vk.nb_public = be64(buf + 72);
+  if (!fr_from_be(vk.coset_shift, buf + 80)) return -1;
+  G1A* pts[8] = {&vk.s[0], &vk.s[1], &vk.s[2], &vk.ql, &vk.qr, &vk.qm, &vk.qo, &vk.qk};
+  for (int i = 0; i < 8; i++)
+    if (decompress_g1(*pts[i], buf + 112 + 32 * i)) return -1;
+  uint32_t nq = be32(buf + 368);
+  size_t off = 372;
+  if (nq > 64 || len < off + 32ull * nq + 160 + 33788 + 8) return -1;
+  vk.qcp.resize(nq);
+  for (uint32_t i = 0; i < nq; i++, off += 32)
+    if (decompress_g1(vk.qcp[i], buf + off)) return -1;
+  if (decompress_g1(vk.g1, buf + off) || decompress_g2(vk.g2[0], buf + off + 32) || decompress_g2(vk.g2[1], buf + off + 96)) return -1;
+  off += 160 + 33788;
+  u64 nidx = be64(buf + off);
+  off += 8;
+  if (nidx > 64 || len < off + 8 * nidx) return -1;
+  vk.cci.resize(nidx);
+  for (u64 i = 0; i < nidx; i++) vk.cci[i] = be64(buf + off + 8 * i);
+  return 0;
+}
+
+static G1A g1_neg(const G1A& p) { return G1A{p.x, -p.y}; }
+// AffineG1::msm: naive sum of AffineG1 * Fr; the result converts to affine (identity panics)
+static bool g1_msm(G1A& out, const std::vector<G1A>& pts, const std::vector<Fr>& ks) {
+  Jac<Fp> acc = jac_identity<Fp>();
+  size_t n = pts.size() < ks.size() ? pts.size() : ks.size();
+  for (size_t i = 0; i < n; i++) {
+    u64 k[4];
+    fr_to_plain(k, ks[i]);
+    acc = jac_add(acc, scalar_mul(pts[i], k));
+  }
+  return to_affine(out, acc);
+}
+static Fr transcript_challenge(const char* id, const uint8_t* prev, const std::vector<std::pair<const uint8_t*, size_t>>& binds,
+                               uint8_t* digest) {
+  Sha256 s;
+  sha_init(s);
+  sha_update(s, id, strlen(id));
+  if (prev) sha_update(s, prev, 32);
+  for (auto& b : binds) sha_update(s, b.first, b.second);
+  sha_final(s, digest);
+  return fr_from_be_mod_order(digest);
+}
+static Fr hash_to_field_bsb22(const uint8_t* pt64) {  // hash_to_field.rs: expand_message_xmd, 48 bytes, mod r
+  static const uint8_t dst[12] = {'B', 'S', 'B', '2', '2', '-', 'P', 'l', 'o', 'n', 'k', 11};
+  uint8_t b0[32], b1[32], b2[32], z[64] = {0}, l[3] = {0, 48, 0}, one = 1, two = 2, x[32];
+  Sha256 s;
+  sha_init(s), sha_update(s, z, 64), sha_update(s, pt64, 64), sha_update(s, l, 3), sha_update(s, dst, 12), sha_final(s, b0);
+  sha_init(s), sha_update(s, b0, 32), sha_update(s, &one, 1), sha_update(s, dst, 12), sha_final(s, b1);
+  for (int i = 0; i < 32; i++) x[i] = b0[i] ^ b1[i];
+  sha_init(s), sha_update(s, x, 32), sha_update(s, &two, 1), sha_update(s, dst, 12), sha_final(s, b2);
+  // BE(b1 | b2[0..16]) mod r = (b1 mod r) * 2^128 + b2_hi
+  Fr hi = fr_from_be_mod_order(b1);
+  u64 t128[4] = {0, 0, 1, 0};
+  uint8_t lo_be[32] = {0};
+  memcpy(lo_be + 16, b2, 16);
+  return fr_add(fr_mul(hi, fr_from_plain(t128)), fr_from_be_mod_order(lo_be));
+}
+
+static int plonk_verify_one(const uint8_t* vk_bytes, size_t vk_len, const uint8_t* pr, size_t len, const uint8_t* inputs_be,
+                            int n_inputs, const uint8_t* rnd_be, uint8_t* dbg_gt) {
+  for (int i = 0; i < n_inputs; i++) {
+    u64 t[4];
+    if (!limbs_from_be(t, inputs_be + 32 * i, MR)) return ST_PANIC_FIELD;
+  }
+  // load_plonk_proof_from_bytes
+  if (len < 516) return ST_PANIC_SHORT;
+  G1A P8[8];
+  int st;
+  for (int i = 0; i < 8; i++)
+    if ((st = load_g1(P8[i], pr + 64 * i))) return st;
+  uint32_t ncl = be32(pr + 512);
+  size_t off = 516;
+  std::vector<Fr> cl;
+  for (uint32_t i = 0; i < ncl; i++) {
+    if (off + 32 > len) return ST_PANIC_SHORT;
+    Fr t;
+    if (!fr_from_be(t, pr + off)) return ST_PANIC_FIELD;
+    cl.push_back(t);
+    off += 32;
+  }
+  if (off + 100 > len) return ST_PANIC_SHORT;
+  const size_t off_zsh = off;
+  G1A zs_h;
+  if ((st = load_g1(zs_h, pr + off))) return st;
+  Fr zu;
+  if (!fr_from_be(zu, pr + off + 64)) return ST_PANIC_FIELD;
+  uint32_t nbsb = be32(pr + off + 96);
+  off += 100;
+  const size_t off_bsb = off;
+  std::vector<G1A> bsb;
+  for (uint32_t i = 0; i < nbsb; i++) {
+    if (off + 64 > len) return ST_PANIC_SHORT;
+    G1A t;
+    if ((st = load_g1(t, pr + off))) return st;
+    bsb.push_back(t);
+    off += 64;
+  }
+  PlonkVk vk;
+  if (parse_plonk_vk(vk, vk_bytes, vk_len)) return ST_PANIC_VK;
+  // verify_plonk
+  if (bsb.size() != vk.qcp.size()) return ST_ERR_BSB22;
+  if ((u64)n_inputs != vk.nb_public) return ST_ERR_WITNESS;
+  uint8_t vkpts[64 * 72], dg[32], dgb[32], dga[32], dgz[32];
+  size_t nvk = 0;
+  {
+    const G1A* pts[8] = {&vk.s[0], &vk.s[1], &vk.s[2], &vk.ql, &vk.qr, &vk.qm, &vk.qo, &vk.qk};
+    for (int i = 0; i < 8; i++) store_g1(vkpts + 64 * nvk++, *pts[i]);
+    for (auto& q : vk.qcp) store_g1(vkpts + 64 * nvk++, q);
+  }
+  Fr gamma = transcript_challenge("gamma", nullptr, {{vkpts, 64 * nvk}, {inputs_be, (size_t)32 * n_inputs}, {pr, 192}}, dg);
+  Fr beta = transcript_challenge("beta", dg, {}, dgb);
+  Fr alpha = transcript_challenge("alpha", dgb, {{pr + off_bsb, 64 * (size_t)nbsb}, {pr + 192, 64}}, dga);
+  Fr zeta = transcript_challenge("zeta", dga, {{pr + 256, 192}}, dgz);
+  const Fr one = fr_one();
+  Fr zeta_n = fr_pow_fr(zeta, fr_from_u64(vk.size));
+  Fr zh_zeta = fr_sub(zeta_n, one);
+  Fr zm1 = fr_sub(zeta, one);
+  if (fr_is_zero(zm1)) return ST_ERR_INVERSE;
+  Fr lagrange_one = fr_mul(fr_mul(fr_inv(zm1), zh_zeta), vk.size_inv);
+  Fr pi = fr_zero();
+  {
+    std::vector<Fr> dens;
+    Fr accw = one;
+    for (int i = 0; i < n_inputs; i++) {
+      dens.push_back(fr_sub(zeta, accw));
+      accw = fr_mul(accw, vk.generator);
+    }
+    // batch_invert (zeros skipped)
+    std::vector<Fr> prod;
+    Fr tmp = one;
+    for (auto& d : dens)
+      if (!fr_is_zero(d)) {
+        tmp = fr_mul(tmp, d);
+        prod.push_back(tmp);
+      }
+    std::vector<Fr> inv(dens.size(), fr_zero());
+    if (!prod.empty()) {
+      tmp = fr_inv(tmp);
+      int k = (int)prod.size() - 1;
+      for (int i = (int)dens.size() - 1; i >= 0; i--) {
+        if (fr_is_zero(dens[i])) continue;
+        Fr sfx = k > 0 ? prod[k - 1] : one;
+        inv[i] = fr_mul(tmp, sfx);
+        tmp = fr_mul(tmp, dens[i]);
+        k--;
+      }
+    }
+    accw = one;
+    for (int i = 0; i < n_inputs; i++) {
+      Fr w;
+      fr_from_be(w, inputs_be + 32 * i);
+      pi = fr_add(pi, fr_mul(fr_mul(fr_mul(fr_mul(zh_zeta, inv[i]), vk.size_inv), accw), w));
+      accw = fr_mul(accw, vk.generator);
+    }
+  }
+  for (size_t i = 0; i < vk.cci.size(); i++) {
+    if (i >= bsb.size()) return ST_PANIC_INDEX;
+    Fr hc = hash_to_field_bsb22(pr + off_bsb + 64 * i);
+    Fr wpi = fr_pow_fr(vk.generator, fr_from_u64(vk.nb_public + vk.cci[i]));
+    Fr den = fr_sub(zeta, wpi);
+    if (fr_is_zero(den)) return ST_PANIC_DIV0;
+    Fr lag = fr_mul(fr_mul(fr_mul(zh_zeta, wpi), fr_inv(den)), vk.size_inv);
+    pi = fr_add(pi, fr_mul(lag, hc));
+  }
+  if (cl.size() < 6) return ST_PANIC_INDEX;
+  const Fr &l = cl[1], &r = cl[2], &o = cl[3], &s1 = cl[4], &s2 = cl[5];
+  Fr a2l1 = fr_mul(fr_mul(lagrange_one, alpha), alpha);
+  Fr t1 = fr_add(fr_add(fr_mul(beta, s1), gamma), l), t2 = fr_add(fr_add(fr_mul(beta, s2), gamma), r);
+  Fr const_lin = fr_mul(fr_mul(fr_mul(fr_mul(t1, t2), fr_add(o, gamma)), alpha), zu);
+  const_lin = fr_neg(fr_add(fr_sub(const_lin, a2l1), pi));
+  if (!fr_eq(const_lin, cl[0])) return ST_ERR_OPENING;
+  Fr s1c = fr_mul(fr_mul(fr_mul(fr_mul(t1, t2), beta), alpha), zu);
+  const Fr& u = vk.coset_shift;
+  Fr bz = fr_mul(beta, zeta), buz = fr_mul(bz, u);
+  Fr s2c = fr_mul(fr_mul(fr_add(fr_add(bz, gamma), l), fr_add(fr_add(buz, gamma), r)), fr_add(fr_add(fr_mul(buz, u), gamma), o));
+  s2c = fr_neg(fr_mul(s2c, alpha));
+  Fr zn2 = fr_pow_fr(zeta, fr_from_u64(vk.size + 2));
+  std::vector<G1A> pts(bsb);
+  for (const G1A* q : {&vk.ql, &vk.qr, &vk.qm, &vk.qo, &vk.qk, &vk.s[2], &P8[3], &P8[4], &P8[5], &P8[6]}) pts.push_back(*q);
+  std::vector<Fr> sc(cl.begin() + 6, cl.end());
+  for (const Fr& k : {l, r, fr_mul(l, r), o, one, s1c, fr_add(a2l1, s2c), fr_neg(zh_zeta), fr_neg(fr_mul(zn2, zh_zeta)),
+                      fr_neg(fr_mul(fr_mul(zn2, zn2), zh_zeta))})
+    sc.push_back(k);
+  G1A lin;
+  if (!g1_msm(lin, pts, sc)) return ST_PANIC_IDENTITY;
+  // kzg::fold_proof
+  std::vector<G1A> digests = {lin, P8[0], P8[1], P8[2], vk.s[0], vk.s[1]};
+  for (auto& q : vk.qcp) digests.push_back(q);
+  if (digests.size() != cl.size()) return ST_ERR_NDIGESTS;
+  uint8_t zb[32], dbytes[64 * 72], dk[32];
+  fr_to_be(zb, zeta);
+  for (size_t i = 0; i < digests.size(); i++) store_g1(dbytes + 64 * i, digests[i]);
+  Fr kg = transcript_challenge("gamma", nullptr, {{zb, 32}, {dbytes, 64 * digests.size()}, {pr + 516, 32 * (size_t)ncl}, {pr + off_zsh + 64, 32}}, dk);
+  std::vector<Fr> gi = {one};
+  for (size_t i = 1; i < digests.size(); i++) gi.push_back(fr_mul(gi.back(), kg));
+  Fr folded_eval = fr_zero();
+  for (size_t i = 0; i < cl.size(); i++) folded_eval = fr_add(folded_eval, fr_mul(cl[i], gi[i]));
+  G1A folded_digest;
+  if (!g1_msm(folded_digest, digests, gi)) return ST_PANIC_IDENTITY;
+  // kzg::batch_verify_multi_points
+  Fr rnd = fr_from_be_mod_order(rnd_be);
+  std::vector<Fr> rn = {one, rnd};
+  std::vector<G1A> quot = {P8[7], zs_h};
+  G1A fq, fdg, t;
+  if (!g1_msm(fq, quot, rn)) return ST_PANIC_IDENTITY;
+  if (!g1_msm(fdg, {folded_digest, P8[3]}, rn)) return ST_PANIC_IDENTITY;
+  Fr fev = fr_add(folded_eval, fr_mul(zu, rnd));
+  {
+    u64 k[4];
+    fr_to_plain(k, fev);
+    if (!to_affine(t, scalar_mul(vk.g1, k))) return ST_PANIC_IDENTITY;
+    if (!to_affine(fdg, jac_add(to_jac(fdg), to_jac(g1_neg(t))))) return ST_PANIC_IDENTITY;
+  }
+  Fr shifted = fr_mul(zeta, vk.generator);
+  std::vector<Fr> rn2 = {zeta, fr_mul(rnd, shifted)};
+  if (!g1_msm(t, quot, rn2)) return ST_PANIC_IDENTITY;
+  if (!to_affine(fdg, jac_add(to_jac(fdg), to_jac(t)))) return ST_PANIC_IDENTITY;
+  fq = g1_neg(fq);
+  G1A ps[2] = {fdg, fq};
+  Fp12 gt = final_exponentiation(miller_product(ps, vk.g2, 2));
+  if (dbg_gt) fp12_to_be(dbg_gt, gt);
+  return gt == fp12_one() ? ST_OK_TRUE : ST_ERR_PAIRING;
+}
+
 extern "C" {
 
 // status[i] as include/bn254v.h (22 = the VK itself failed to parse: the reference would panic on every call)
@@ -917,6 +1264,17 @@ int ref_groth16_synth(u64 seed, int n_public, int sign_mode, size_t first, size_
     store_g1(proofs + 256 * ii, pa), store_g2(proofs + 256 * ii + 64, pb), store_g1(proofs + 256 * ii + 192, pc);
     for (int i = 0; i < n_public; i++) limbs_to_be(inputs_be + (ii * n_public + i) * 32, xs[i]);
     expected[ii] = bad ? ST_OK_FALSE : ST_OK_TRUE;
+  });
+  return 0;
+}
+
+int ref_plonk_verify_batch(const uint8_t* vk, size_t vk_len, const uint8_t* proofs, size_t stride, const uint32_t* lens,
+                            const uint8_t* inputs_be, int n_inputs, const uint8_t* rnd_be, size_t n, uint8_t* status,
+                            uint8_t* dbg_gt, int threads) {
+  parallel_for(n, threads, [&](size_t i) {
+    status[i] = (uint8_t)plonk_verify_one(vk, vk_len, proofs + stride * i, lens ? lens[i] : stride,
+                                          inputs_be + (size_t)32 * n_inputs * i, n_inputs, rnd_be + 32 * i,
+                                          dbg_gt ? dbg_gt + 384 * i : 0);
   });
   return 0;
 }

@@ -26,6 +26,8 @@ def lib(count=False):
         L.ref_pairing_product_batch.argtypes = [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_void_p, c_int]
         L.ref_groth16_synth.argtypes = [c_uint64, c_int, c_int, c_size_t, c_size_t, c_void_p, POINTER(c_size_t), c_void_p,
                                         c_void_p, c_void_p, c_int]
+        L.ref_plonk_verify_batch.argtypes = [c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_void_p,
+                                             c_size_t, c_void_p, c_void_p, c_int]
         L.ref_fp_mul_count.restype = c_uint64
         _libs[name] = L
     return _libs[name]
@@ -78,3 +80,21 @@ def groth16_synth(seed, n, n_public=2, sign_mode=0, first_index=0, threads=0):
                              _p(inputs), _p(expected), threads)
     assert rc == 0
     return bytes(vk[:vk_len.value]), proofs, inputs, expected
+
+
+def plonk_verify_batch(vk, proofs, inputs, rnd, threads=1, lens=None, want_gt=False):
+    """Reference-shaped PlonkVerifier::verify over a batch.  Returns (seconds, status[, gt])."""
+    L = lib()
+    vkb = np.frombuffer(bytes(vk), dtype=np.uint8)
+    proofs = np.ascontiguousarray(proofs, dtype=np.uint8)
+    inputs = np.ascontiguousarray(inputs, dtype=np.uint8)
+    rnd = np.ascontiguousarray(rnd, dtype=np.uint8)
+    n = proofs.shape[0]
+    status = np.full(n, 255, dtype=np.uint8)
+    gt = np.zeros((n, 384), np.uint8) if want_gt else None
+    lens = None if lens is None else np.ascontiguousarray(lens, dtype=np.uint32)
+    t0 = time.perf_counter()
+    L.ref_plonk_verify_batch(_p(vkb), vkb.size, _p(proofs), proofs.shape[1], _p(lens), _p(inputs), inputs.shape[1], _p(rnd),
+                             n, _p(status), _p(gt), threads)
+    dt = time.perf_counter() - t0
+    return (dt, status, gt) if want_gt else (dt, status)

@@ -52,3 +52,32 @@ def test_malformed_classes():
         inputs = np.array([[np.frombuffer(int(x).to_bytes(32, "big"), np.uint8) for x in xs]])
         _, st = ref_cpu.groth16_verify_batch(vk, proofs, inputs)
         assert st[0] == names[want], name
+
+
+def test_plonk_port_fixtures_and_mutation_map():
+    """The C++ PlonK restatement: bundled fixtures Ok(true) with the golden GT value, and the status of every committed
+    mutated proof (4 programs x 24 classes), i.e. the same map the Python oracle produced."""
+    import workloads
+    from helpers import PLONK_STATUS, plonk_fixture
+    vk = workloads.plonk_vk_bytes()
+    gold = load_json("plonk_golden.json")
+    for prog, g in gold.items():
+        pr, xs = plonk_fixture(prog)
+        proofs = np.frombuffer(pr, np.uint8).reshape(1, -1)
+        inputs = np.array([[np.frombuffer(x.to_bytes(32, "big"), np.uint8) for x in xs]])
+        rnd = np.frombuffer(int(g["rnd"], 16).to_bytes(32, "big"), np.uint8).reshape(1, 32)
+        _, st, gt = ref_cpu.plonk_verify_batch(vk, proofs, inputs, rnd, want_gt=True)
+        assert st[0] == 0 and gt[0].tobytes().hex() == g["gt"]
+    muts = load_json("plonk_mutations.json")
+    stride = max(len(m["raw_proof"]) // 2 for m in muts)
+    proofs = np.zeros((len(muts), stride), np.uint8)
+    lens = np.zeros(len(muts), np.uint32)
+    for i, m in enumerate(muts):
+        b = bytes.fromhex(m["raw_proof"])
+        proofs[i, :len(b)] = np.frombuffer(b, np.uint8)
+        lens[i] = len(b)
+    inputs = np.array([[np.frombuffer(int(s).to_bytes(32, "big"), np.uint8) for s in m["inputs"]] for m in muts])
+    rnd = np.tile(np.frombuffer((77).to_bytes(32, "big"), np.uint8), (len(muts), 1))
+    _, st = ref_cpu.plonk_verify_batch(vk, proofs, inputs, rnd, threads=4, lens=lens)
+    for m, s in zip(muts, st):
+        assert s == PLONK_STATUS[m["status"]], (m["program"], m["mutation"])
