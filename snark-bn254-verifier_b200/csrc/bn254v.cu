@@ -143,6 +143,7 @@ struct bn254v_batch {
   struct Part {
     size_t lo, hi;
     uint8_t *proofs, *inputs, *status;
+    Fp12* fbuf;
   };
   std::vector<Part> parts;
 };
@@ -297,6 +298,39 @@ __global__ void __launch_bounds__(TPB, 1)
   if (live && !(threadIdx.x & 1)) status[i] = (uint8_t)st;
 }
 
+// Groth16 as two launches (groth16.cuh): Miller values travel through `fbuf` (384 B per proof); a proof that failed
+// in the first half keeps its status, the others are marked BN254V_STATUS_UNSET until the second half decides.
+template <int TPB>
+__global__ void __launch_bounds__(TPB, 1)
+    k_groth16_miller(const Groth16VkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride,
+                     const uint32_t* __restrict__ proof_len, const uint8_t* __restrict__ inputs, int n_inputs, size_t n,
+                     uint8_t* __restrict__ status, Fp12* __restrict__ fbuf, uint8_t* dbg_l, uint8_t* dbg_m) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Groth16Debug dbg{dbg_l ? dbg_l + 64 * i : nullptr, dbg_m ? dbg_m + 384 * i : nullptr, nullptr};
+  uint32_t len = proof_len ? proof_len[i] : (uint32_t)stride;
+  if (len > stride) len = (uint32_t)stride;
+  Fp12 f;
+  int st = groth16_miller_one(f, *vk, proofs + stride * i, len, inputs + (size_t)32 * n_inputs * i, n_inputs, dbg);
+  if (st == BN254V_OK_TRUE) {
+    fbuf[i] = f;
+    status[i] = BN254V_STATUS_UNSET;
+  } else {
+    status[i] = (uint8_t)st;
+  }
+}
+template <int TPB>
+__global__ void __launch_bounds__(TPB, 1)
+    k_groth16_finish(const Groth16VkDev* __restrict__ vk, size_t n, uint8_t* __restrict__ status,
+                     const Fp12* __restrict__ fbuf, uint8_t* dbg_gt) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (status[i] != BN254V_STATUS_UNSET) return;
+  Groth16Debug dbg{nullptr, nullptr, dbg_gt ? dbg_gt + 384 * i : nullptr};
+  Fp12 f = fbuf[i];
+  status[i] = (uint8_t)groth16_finish_one(f, *vk, dbg);
+}
+
 template <int KP, int TPB>
 __global__ void __launch_bounds__(TPB, 1)
     k_pairing_product(const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2, size_t n,
@@ -349,7 +383,23 @@ static int pick_shape(size_t m) {
 
 static void launch_groth16_verify(cudaStream_t st, const Groth16VkDev* vk, const uint8_t* proofs, size_t stride,
                                   const uint32_t* lens, const uint8_t* inputs, int n_inputs, size_t m, uint8_t* status,
-                                  uint8_t* l, uint8_t* ml, uint8_t* gt) {
+                                  uint8_t* l, uint8_t* ml, uint8_t* gt, Fp12* fbuf = nullptr) {
+  // Big batches: two launches (Miller loop | final exponentiation), each with about half the code and stack of the fused
+  // kernel -- measured 2 % faster at 2^16 and 2^18.  BN254V_VARIANT=42 / 43 force the fused 448 / 384 kernels.
+  const int shape = pick_shape(m);
+  if (fbuf && (shape == 3 || shape == 10)) {
+    if (shape == 3) {
+      k_groth16_miller<448><<<(unsigned)((m + 447) / 448), 448, 0, st>>>(vk, proofs, stride, lens, inputs, n_inputs, m,
+                                                                        status, fbuf, l, ml);
+      k_groth16_finish<448><<<(unsigned)((m + 447) / 448), 448, 0, st>>>(vk, m, status, fbuf, gt);
+    } else {
+      k_groth16_miller<384><<<(unsigned)((m + 383) / 384), 384, 0, st>>>(vk, proofs, stride, lens, inputs, n_inputs, m,
+                                                                        status, fbuf, l, ml);
+      k_groth16_finish<384><<<(unsigned)((m + 383) / 384), 384, 0, st>>>(vk, m, status, fbuf, gt);
+    }
+    g_launches++;  // (the caller counts the other one)
+    return;
+  }
 #define LV(TPB, MINB)                                                                                              \
   k_groth16_verify<TPB, MINB><<<(unsigned)((m + TPB - 1) / TPB), TPB, 0, st>>>(vk, proofs, stride, lens, inputs, \
                                                                                n_inputs, m, status, l, ml, gt)
@@ -365,7 +415,8 @@ static void launch_groth16_verify(cudaStream_t st, const Groth16VkDev* vk, const
 #undef LVP
   switch (pick_shape(m)) {
     case 2: LV(128, 4); break;
-    case 3: LV(448, 1); break;
+    case 3: case 42: LV(448, 1); break;
+    case 43: LV(384, 1); break;
     case 6: LV(32, 1); break;
     case 10: LV(384, 1); break;
     default: LV(128, 2); break;
@@ -646,7 +697,7 @@ int bn254v_groth16_verify_batch(const bn254v_vk* vk, const uint8_t* proofs, size
   if (n == 0) return BN254V_SUCCESS;
   const int nd = (int)g_devs.size();
   struct Part {
-    DevBuf proofs, lens, inputs, status, l, m, gt;
+    DevBuf proofs, lens, inputs, status, l, m, gt, fbuf;
   };
   std::vector<Part> parts(nd);
   const size_t in_bytes = (size_t)32 * n_inputs;
@@ -671,9 +722,11 @@ int bn254v_groth16_verify_batch(const bn254v_vk* vk, const uint8_t* proofs, size
     if (dbg && dbg->g1_out) CU(p.l.alloc(m * 64));
     if (dbg && dbg->miller_out) CU(p.m.alloc(m * 384));
     if (dbg && dbg->gt_out) CU(p.gt.alloc(m * 384));
+    CU(p.fbuf.alloc(m * sizeof(Fp12)));
     launch_groth16_verify(dev.stream, (const Groth16VkDev*)vk->dev[d], p.proofs.as<uint8_t>(), proof_stride,
                           proof_len ? p.lens.as<uint32_t>() : nullptr, p.inputs.as<uint8_t>(), n_inputs, m,
-                          p.status.as<uint8_t>(), p.l.as<uint8_t>(), p.m.as<uint8_t>(), p.gt.as<uint8_t>());
+                          p.status.as<uint8_t>(), p.l.as<uint8_t>(), p.m.as<uint8_t>(), p.gt.as<uint8_t>(),
+                          p.fbuf.as<Fp12>());
     g_launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(status + lo, p.status.p, m, cudaMemcpyDeviceToHost, dev.stream));
@@ -865,12 +918,14 @@ int bn254v_groth16_batch_upload(const bn254v_vk* vk, const uint8_t* proofs, size
     shard(n, d, nd, p.lo, p.hi);
     size_t m = p.hi - p.lo;
     p.proofs = p.inputs = p.status = nullptr;
+    p.fbuf = nullptr;
     if (!m) continue;
     Dev& dev = g_devs[d];
     cudaError_t e = cudaSetDevice(dev.id);
     if (e == cudaSuccess) e = cudaMalloc(&p.proofs, m * 256);
     if (e == cudaSuccess) e = cudaMalloc(&p.inputs, m * in_bytes + 1);
     if (e == cudaSuccess) e = cudaMalloc(&p.status, m);
+    if (e == cudaSuccess) e = cudaMalloc(&p.fbuf, m * sizeof(Fp12));
     if (e == cudaSuccess)
       e = cudaMemcpy2DAsync(p.proofs, 256, proofs + p.lo * proof_stride, proof_stride, 256, m, cudaMemcpyHostToDevice,
                             dev.stream);
@@ -898,7 +953,7 @@ int bn254v_groth16_batch_verify(const bn254v_vk* vk, bn254v_batch* b, uint8_t* s
     CU(cudaEventRecord(dev.ev0, dev.stream));
     if (m) {
       launch_groth16_verify(dev.stream, (const Groth16VkDev*)vk->dev[d], p.proofs, 256, nullptr, p.inputs,
-                            b->n_inputs, m, p.status, nullptr, nullptr, nullptr);
+                            b->n_inputs, m, p.status, nullptr, nullptr, nullptr, p.fbuf);
       g_launches++;
       CU(cudaGetLastError());
     }
@@ -932,6 +987,7 @@ void bn254v_batch_free(bn254v_batch* b) {
     cudaFree(b->parts[d].proofs);
     cudaFree(b->parts[d].inputs);
     cudaFree(b->parts[d].status);
+    cudaFree(b->parts[d].fbuf);
   }
   delete b;
 }

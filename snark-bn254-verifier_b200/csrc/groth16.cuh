@@ -90,7 +90,10 @@ struct Groth16Debug {
 };
 
 // proof: >= 256 bytes (A | B | C), proof_len: valid bytes.
-HD int groth16_verify_one(const Groth16VkDev& vk, const uint8_t* proof, uint32_t proof_len,
+// The verification in two halves, so that the batch kernels can run them as two launches (each with half the code
+// and half the stack): (1) decode, validate, prepare_inputs, Miller loop -> the Fq12 Miller value;
+// (2) final exponentiation and comparison with e(alpha, beta').
+HD int groth16_miller_one(Fp12& f, const Groth16VkDev& vk, const uint8_t* proof, uint32_t proof_len,
                           const uint8_t* inputs_be, int n_inputs, const Groth16Debug& dbg) {
   if (proof_len < 256) return BN254V_PANIC_SHORT_BUFFER;
   G1Aff A, C;
@@ -109,12 +112,23 @@ HD int groth16_verify_one(const Groth16VkDev& vk, const uint8_t* proof, uint32_t
 
   G1Aff pf[2] = {L, C};
   const Line* tabs[2] = {vk.gamma_lines, vk.delta_lines};
-  Fp12 f;
   miller_loop<1, 2>(f, &A, &B, pf, tabs);
   if (dbg.miller) fp12_to_bytes(dbg.miller, f);
+  return BN254V_OK_TRUE;
+}
+HD int groth16_finish_one(Fp12& f, const Groth16VkDev& vk, const Groth16Debug& dbg) {
   final_exponentiation(f, f);
   if (dbg.gt) fp12_to_bytes(dbg.gt, f);
   return eq(f, vk.target) ? BN254V_OK_TRUE : BN254V_OK_FALSE;
+}
+
+// proof: >= 256 bytes (A | B | C), proof_len: valid bytes.
+HD int groth16_verify_one(const Groth16VkDev& vk, const uint8_t* proof, uint32_t proof_len,
+                          const uint8_t* inputs_be, int n_inputs, const Groth16Debug& dbg) {
+  Fp12 f;
+  int st = groth16_miller_one(f, vk, proof, proof_len, inputs_be, n_inputs, dbg);
+  if (st != BN254V_OK_TRUE) return st;
+  return groth16_finish_one(f, vk, dbg);
 }
 
 // Raw k-pair product (bn::pairing_batch): all G2 variable.  A pair whose G1 bytes are all zero is
