@@ -97,7 +97,7 @@ def ncu_traffic(n):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
-        t = json.load(open(p))["k_groth16_verify"]
+        t = json.load(open(p))["k_groth16_miller"]
         return t["dram_bytes_per_launch"] if t["batch"] == n else None
     except Exception:
         return None
@@ -283,13 +283,14 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     launches0 = pkg.launch_count()
-    kernel_ms = []
+    kernel_ms, split_ms = [], []
     t0 = time.perf_counter()
     for _ in range(args.steps):
         flush.zero_()
         torch.cuda.synchronize()
         st, ms = batch.verify(want_status=False)
         kernel_ms.append(ms)
+        split_ms.append(pkg.last_kernel_split())
     barrier()
     wall_kernel = time.perf_counter() - t0
     launches = pkg.launch_count() - launches0
@@ -321,11 +322,25 @@ def run_b200(args):
 
     work = work_per_proof()
     macs_per_proof = work.get("groth16_macs", work["groth16_fp_mul"] * MACS_PER_FPMUL)
-    achieved = macs_per_proof * n * args.steps / (sum(kernel_ms) * 1e-3)  # this rank's kernel
+    step_achieved = macs_per_proof * n * args.steps / (sum(kernel_ms) * 1e-3)  # both launches of this rank's step
+    miller_ms = sum(a for a, b in split_ms)
+    finish_ms = sum(b for a, b in split_ms)
+    two = finish_ms > 0
+    # dominant kernel: the Miller-loop launch (its own algorithmic MACs over its own CUDA-event duration)
+    dom_macs = work.get("groth16_miller_macs", macs_per_proof) if two else macs_per_proof
+    achieved = dom_macs * n * args.steps / (miller_ms * 1e-3)
     roofline = {
         "bound": "int32-imad", "achieved": achieved / 1e12, "peak": peak["wide_mac_per_s"] / 1e12, "unit": "TMAC/s",
         "frac": achieved / peak["wide_mac_per_s"], "traffic": ncu_traffic(n),
-        "kernel": "k_groth16_verify", "macs_per_proof": macs_per_proof, "fp_mul_per_proof": work["groth16_fp_mul"],
+        "kernel": "k_groth16_miller<448>" if two else "k_groth16_verify",
+        "kernel_ms_per_launch": miller_ms / args.steps, "macs_per_launch": dom_macs * n,
+        "share_of_step": miller_ms / sum(kernel_ms),
+        "step": {"achieved": step_achieved / 1e12, "frac": step_achieved / peak["wide_mac_per_s"],
+                 "kernels": ["k_groth16_miller", "k_groth16_finish"] if two else ["k_groth16_verify"],
+                 "finish_ms_per_launch": finish_ms / args.steps,
+                 "finish_frac": (work.get("groth16_finish_macs", 0) * n * args.steps / (finish_ms * 1e-3) /
+                                 peak["wide_mac_per_s"]) if two else None},
+        "macs_per_proof": macs_per_proof, "fp_mul_per_proof": work["groth16_fp_mul"],
         "peak_source": "measured live: bn254v_imad_peak (independent IMAD.WIDE.U32 accumulate chains, 8 warps/SMSP, "
                        "all SMs); MEASURED_PEAKS.json holds no integer peak",
         "peak_imad32_tmacs": peak["lo_mac_per_s"] / 1e12,

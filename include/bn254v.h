@@ -149,6 +149,9 @@ int bn254v_pairing_synth(uint64_t seed, int k, size_t first_index, size_t n, uin
 /* Dependent-free IMAD.WIDE.U32 stream on device 0: returns achieved multiply-adds per second
  * (the int32 roofline denominator).  iters >= 1.                                 */
 int bn254v_imad_peak(int iters, double* wide_mac_per_s, double* lo_mac_per_s, float* sm_clock_mhz);
+/* Device times (CUDA events, device slot 0) of the two launches of the last bn254v_groth16_batch_verify: the Miller-loop
+ * kernel and the final-exponentiation kernel (finish_ms = 0 when the batch ran as one fused launch).              */
+int bn254v_last_kernel_split(float* miller_ms, float* finish_ms);
 /* Number of kernel launches issued by this library since init (for bench.py's gpu_launches).    */
 uint64_t bn254v_launch_count(void);
 

@@ -39,6 +39,7 @@ EXPORTS = [
     "bn254v_groth16_verify_batch", "bn254v_plonk_verify_batch", "bn254v_pairing_product_batch",
     "bn254v_groth16_batch_upload", "bn254v_groth16_batch_verify", "bn254v_batch_free",
     "bn254v_groth16_synth", "bn254v_pairing_synth", "bn254v_imad_peak", "bn254v_launch_count",
+    "bn254v_last_kernel_split",
 ]
 
 
@@ -133,6 +134,8 @@ def load_library():
     lib.bn254v_imad_peak.argtypes = [c_int, POINTER(c_double), POINTER(c_double), POINTER(c_float)]
     lib.bn254v_imad_peak.restype = c_int
     lib.bn254v_launch_count.restype = c_uint64
+    lib.bn254v_last_kernel_split.argtypes = [POINTER(c_float), POINTER(c_float)]
+    lib.bn254v_last_kernel_split.restype = c_int
     _lib = lib
     return lib
 
@@ -419,6 +422,13 @@ class Groth16DeviceBatch:
             self.free()
         except Exception:
             pass
+
+
+def last_kernel_split():
+    """(Miller-loop kernel ms, final-exponentiation kernel ms) of the last Groth16DeviceBatch.verify()."""
+    a, b = c_float(0), c_float(0)
+    _check(load_library().bn254v_last_kernel_split(ctypes.byref(a), ctypes.byref(b)))
+    return a.value, b.value
 
 
 def imad_peak(iters=4096):

@@ -34,6 +34,22 @@ int hs_pairing_product(int k, const uint8_t* g1, const uint8_t* g2, uint8_t* mil
   return -1;
 }
 
+// final exponentiation of a canonical Fq12 value (work counting)
+void hs_final_exp_only(const uint8_t* f_be) {
+  Fp12 f;
+  Fp2* cs[6] = {&f.c0.c0, &f.c0.c1, &f.c0.c2, &f.c1.c0, &f.c1.c1, &f.c1.c2};
+  for (int i = 0; i < 6; i++) {
+    fp_load_be(cs[i]->c0, f_be + 64 * i);
+    fp_load_be(cs[i]->c1, f_be + 64 * i + 32);
+  }
+  unsigned long long before = 0;
+#ifdef BN254_COUNT_MULS
+  before = fe_mac_counter();
+  fe_mac_counter() = 0;
+#endif
+  final_exponentiation(f, f);
+  (void)before;
+}
 int hs_g2_check(const uint8_t* g2) {
   G2Aff q;
   return load_g2_checked(q, g2);

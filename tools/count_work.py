@@ -44,6 +44,12 @@ def main(write=True):
         n += 1
     out["groth16_macs"] = hs.hs_mul_count(1) // n
     out["groth16_fp_mul"] = out["groth16_macs"] // 136
+    # split at the kernel boundary: the final exponentiation alone (same Fq12 chain for every input)
+    c = load_json("pairing_golden.json")[0]
+    hs.hs_mul_count(1)
+    hs.hs_final_exp_only(bytes.fromhex(c["miller"]))
+    out["groth16_finish_macs"] = hs.hs_mul_count(1)
+    out["groth16_miller_macs"] = out["groth16_macs"] - out["groth16_finish_macs"]
     # raw pairing products
     for c in load_json("pairing_golden.json"):
         if c["is_one"]:
