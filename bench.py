@@ -349,7 +349,7 @@ def run_b200(args):
     }
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # reported at N=1 only
         try:
             cores = host_cores()
             sample = args.cpu_sample or max(cores * 512, 512)
@@ -362,7 +362,7 @@ def run_b200(args):
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "unavailable: %r" % (e,)}
 
     extra = {}
-    if not args.no_secondary:
+    if not args.no_secondary and world == 1:
         extra = secondary_workloads(pkg, work)
 
     line = {
