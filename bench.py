@@ -196,9 +196,12 @@ def secondary_workloads(pkg, work):
     # the same records 8x: 2^17 proofs fill the GPU (2^14 leaves the final pairing stage at <1 warp per SMSP)
     big = 8
     pb, ib, rb, eb = (np.tile(x, (big,) + (1,) * (x.ndim - 1)) for x in (proofs, inputs, rnd, expected))
-    t0 = time.perf_counter()
-    st = pkg.PlonkVerifier.verify_batch(pb, vk, ib, rnd=rb)
-    dt = time.perf_counter() - t0
+    dt = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        st = pkg.PlonkVerifier.verify_batch(pb, vk, ib, rnd=rb)
+        d1 = time.perf_counter() - t0
+        dt = d1 if dt is None else min(dt, d1)
     assert (st == eb).all()
     out["plonk"]["e2e_proofs_per_sec_2e17_batch"] = n * big / dt
     try:  # CPU side by side: the oracle's C++ restatement of PlonkVerifier::verify on the same records

@@ -72,20 +72,12 @@ HD bool eq(const Fp2& a, const Fp2& b) {
   int z = fe_eq(a.c, b.c);
   return z & __shfl_xor_sync(pair_mask(), z, 1);
 }
-HD Fp fe_p_minus(const Fp& b) {  // p - b for b in [0, p): in (0, p], a valid (< 2p) multiplier operand
-  Fp r;
-  r.v[0] = cc::sub_cc(FpCfg::mod(0), b.v[0]);
-#pragma unroll
-  for (int i = 1; i < 7; i++) r.v[i] = cc::subc_cc(FpCfg::mod(i), b.v[i]);
-  r.v[7] = cc::subc(FpCfg::mod(7), b.v[7]);
-  return r;
-}
 // lane0: a0 b0 - a1 b1 = a0 b0 + a1 (p - b1);  lane1: a1 b0 + a0 b1.  Both are own*U + other*V with
 // (U, V) = (b_own, p - b_other) on lane0 and (b_other, b_own) on lane1; the sum of the two wide products is < 2 p^2.
 HDN Fp2 mul(Fp2 a, Fp2 b) {
   const bool h = lane_h();
   Fp oa = xchg(a.c), ob = xchg(b.c);
-  Fp U = sel(h, ob, b.c), V = sel(h, b.c, fe_p_minus(ob));
+  Fp U = sel(h, ob, b.c), V = sel(h, b.c, fe_mod_minus(ob));
   uint32_t T0[16], T1[16];
   fe_mul_wide(T0, a.c, U);
   fe_mul_wide(T1, oa, V);
@@ -106,9 +98,7 @@ HD Fp2 scale(const Fp2& a, const Fp& k) { return Fp2{fe_mul(a.c, k)}; }
 // (9 + u)(a0 + a1 u) = (9 a0 - a1) + (9 a1 + a0) u
 HDN Fp2 mul_xi(Fp2 a) {
   Fp oa = xchg(a.c);
-  Fp w = sel(lane_h(), oa, fe_neg(oa));
-  Fp t = fe_dbl(fe_dbl(fe_dbl(a.c)));
-  return Fp2{fe_add(fe_add(t, a.c), w)};
+  return Fp2{fe_mul9_add(a.c, sel(lane_h(), oa, fe_mod_minus(oa)))};
 }
 HDN Fp2 inv(Fp2 a) {
   Fp s = fe_sqr(a.c);
@@ -116,7 +106,7 @@ HDN Fp2 inv(Fp2 a) {
   Fp r = fe_mul(a.c, n);
   return Fp2{sel(lane_h(), fe_neg(r), r)};
 }
-HD Fp2 fp2_halve(const Fp2& a) { return scale(a, fp_two_inv()); }
+HD Fp2 fp2_halve(const Fp2& a) { return Fp2{fe_halve(a.c)}; }
 HD Fp2 lane_const(const Fp& c0, const Fp& c1) { return Fp2{sel(lane_h(), c1, c0)}; }
 HD Fp2 fp2_b2() {
   Fp c0, c1;

@@ -34,7 +34,7 @@ HD Fp fp_three() {
   BN_LOAD_FP(r, K::three, 0);
   return r;
 }
-HD Fp fp_halve(const Fp& a) { return fe_mul(a, fp_two_inv()); }
+HD Fp fp_halve(const Fp& a) { return fe_halve(a); }
 
 // ------------------------------------------------------------------------------------------ Fp2
 struct Fp2 {
@@ -78,15 +78,13 @@ HDN Fp2 sqr(Fp2 a) {
 HD Fp2 scale(const Fp2& a, const Fp& k) { return Fp2{fe_mul(a.c0, k), fe_mul(a.c1, k)}; }
 // multiply by xi = 9 + u: (9 a0 - a1) + (a0 + 9 a1) u
 HDN Fp2 mul_xi(Fp2 a) {
-  Fp t0 = fe_dbl(fe_dbl(fe_dbl(a.c0)));  // 8 a0
-  Fp t1 = fe_dbl(fe_dbl(fe_dbl(a.c1)));  // 8 a1
-  return Fp2{fe_sub(fe_add(t0, a.c0), a.c1), fe_add(fe_add(t1, a.c1), a.c0)};
+  return Fp2{fe_mul9_add(a.c0, fe_mod_minus(a.c1)), fe_mul9_add(a.c1, a.c0)};
 }
 HD Fp2 inv(const Fp2& a) {
   Fp n = fe_inv(fe_add(fe_sqr(a.c0), fe_sqr(a.c1)));
   return Fp2{fe_mul(a.c0, n), fe_neg(fe_mul(a.c1, n))};
 }
-HD Fp2 fp2_halve(const Fp2& a) { return scale(a, fp_two_inv()); }
+HD Fp2 fp2_halve(const Fp2& a) { return Fp2{fe_halve(a.c0), fe_halve(a.c1)}; }
 
 #define BN_LOAD_FP2(dst, fn, idx) \
   {                               \

@@ -165,6 +165,18 @@ void hs_fp2_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {  // 16 word
   Fp2 z = mul(x, y);
   memcpy(r, z.c0.v, 32), memcpy(r + 8, z.c1.v, 32);
 }
+void hs_fp2_mul_xi(uint32_t* r, const uint32_t* a) {
+  Fp2 x;
+  memcpy(x.c0.v, a, 32), memcpy(x.c1.v, a + 8, 32);
+  Fp2 z = mul_xi(x);
+  memcpy(r, z.c0.v, 32), memcpy(r + 8, z.c1.v, 32);
+}
+void hs_fp_halve(uint32_t* r, const uint32_t* a) {
+  Fp x;
+  memcpy(x.v, a, 32);
+  Fp z = fe_halve(x);
+  memcpy(r, z.v, 32);
+}
 void hs_fp2_sqr(uint32_t* r, const uint32_t* a) {
   Fp2 x;
   memcpy(x.c0.v, a, 32), memcpy(x.c1.v, a + 8, 32);

@@ -66,6 +66,12 @@ def test_fp2_mul_sqr_lazy_reduction_edge_cases(hs):
         assert val(out) == (c0, c1), (a0, a1, b0, b1)
         hs.hs_fp2_sqr(out, words(a0, a1))
         assert val(out) == ((a0 * a0 - a1 * a1) * rinv % bo.P, 2 * a0 * a1 * rinv % bo.P)
+        # (9 + u)(a0 + a1 u) through the multiply-by-9 / estimated-quotient path (linear: representation-agnostic)
+        hs.hs_fp2_mul_xi(out, words(a0, a1))
+        assert val(out) == ((9 * a0 - a1) % bo.P, (9 * a1 + a0) % bo.P), (a0, a1)
+        h = (ctypes.c_uint32 * 8)()
+        hs.hs_fp_halve(h, (ctypes.c_uint32 * 8)(*[(a0 >> (32 * i)) & 0xFFFFFFFF for i in range(8)]))
+        assert sum(int(h[i]) << (32 * i) for i in range(8)) == a0 * pow(2, -1, bo.P) % bo.P
 
 
 def test_pairing_products_match_golden(hs):
