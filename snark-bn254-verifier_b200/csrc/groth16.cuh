@@ -31,12 +31,14 @@ struct Groth16VkDev {
   Fp12 target;               // e(alpha, beta')
   Line gamma_lines[BN_N_LINES];
   Line delta_lines[BN_N_LINES];
+  LinePairKF gd_pairs[BN_N_LINES];  // product coefficients of the gamma and delta lines (pairing_body.inc)
 };
 
 // VK-constant precomputation (runs once per VK, single thread).
 HD void groth16_vk_prepare(Groth16VkDev& vk) {
   g2_precompute(vk.gamma_lines, vk.gamma);
   g2_precompute(vk.delta_lines, vk.delta);
+  line_pair_table(vk.gd_pairs, vk.gamma_lines, vk.delta_lines);
   Fp12 f;
   miller_loop<1, 0>(f, &vk.alpha, &vk.beta, nullptr, nullptr);
   final_exponentiation(vk.target, f);
@@ -111,8 +113,7 @@ HD int groth16_miller_one(Fp12& f, const Groth16VkDev& vk, const uint8_t* proof,
   if (dbg.L) store_g1(dbg.L, L);
 
   G1Aff pf[2] = {L, C};
-  const Line* tabs[2] = {vk.gamma_lines, vk.delta_lines};
-  miller_loop<1, 2>(f, &A, &B, pf, tabs);
+  miller_loop_pairtab<1>(f, &A, &B, pf, vk.gd_pairs);
   if (dbg.miller) fp12_to_bytes(dbg.miller, f);
   return BN254V_OK_TRUE;
 }

@@ -185,9 +185,12 @@ struct Line {
 };
 HD Line lane_line(const LineF& l) { return Line{ld2(l.ell_0), ld2(l.ell_vw), ld2(l.ell_vv)}; }
 
+typedef bn254::LinePairKF LinePairKF;
 #define BN_LD_LINE(l) lane_line(l)
+#define BN_LD_FP2(x) ld2(x)
 #include "pairing_body.inc"
 #undef BN_LD_LINE
+#undef BN_LD_FP2
 
 // ---- wire format: x1 | x0 | y1 | y0, each lane reads its own component
 HD bool load_g2_lane(G2Aff& q, const uint8_t* b) {

@@ -32,6 +32,7 @@ struct PlonkVkDev {
   uint8_t kzg_vk_bytes[64 * (2 + BN_MAX_QCP)];  // canonical S1 | S2 | Qcp..  (KZG transcript)
   const G1Aff* fixed_tables;                 // [7 + n_qcp + 1][32][255] window tables of the VK bases, or null
   Line g2_lines[2][BN_N_LINES];
+  LinePairKF g2_pairs[BN_N_LINES];           // product coefficients of the two KZG G2 line tables
 };
 
 // VK-constant MSM bases, in table order: Ql Qr Qm Qo S3 S1 S2 Qcp.. g1(KZG)
@@ -53,6 +54,7 @@ HD const G1Aff& plonk_fixed_base(const PlonkVkDev& vk, int idx) {
 HD void plonk_vk_prepare(PlonkVkDev& vk) {
   g2_precompute(vk.g2_lines[0], vk.g2[0]);
   g2_precompute(vk.g2_lines[1], vk.g2[1]);
+  line_pair_table(vk.g2_pairs, vk.g2_lines[0], vk.g2_lines[1]);
 }
 
 // ---- Fr helpers (Montgomery unless said otherwise)
@@ -488,9 +490,8 @@ HD int plonk_stage_e(PlonkWork& w, const PlonkVkDev& vk, const uint8_t* pr, cons
     store_g1(dbg.g1 + 128, pf[0]);
     store_g1(dbg.g1 + 192, pf[1]);
   }
-  const Line* tabs[2] = {vk.g2_lines[0], vk.g2_lines[1]};
   Fp12 f;
-  miller_loop<0, 2>(f, nullptr, nullptr, pf, tabs);
+  miller_loop_pairtab<0>(f, nullptr, nullptr, pf, vk.g2_pairs);
   if (dbg.miller) fp12_to_bytes(dbg.miller, f);
   final_exponentiation(f, f);
   if (dbg.gt) fp12_to_bytes(dbg.gt, f);
