@@ -437,3 +437,27 @@ def imad_peak(iters=4096):
     wide, lo, clk = c_double(0), c_double(0), c_float(0)
     _check(lib.bn254v_imad_peak(iters, ctypes.byref(wide), ctypes.byref(lo), ctypes.byref(clk)))
     return {"wide_mac_per_s": wide.value, "lo_mac_per_s": lo.value, "sm_clock_mhz": clk.value}
+
+
+def verify_many(items, rnd=None):
+    """Mixed batch over several verifying keys and both proof systems: `items` is a list of
+    (kind, proof_bytes, vk_bytes, public_inputs) with kind in {"groth16", "plonk"}.  Items are grouped by
+    (kind, sha256(vk)) -- one device batch per group, VK handles cached -- and the status bytes come back in input order.
+    `rnd`: optional per-item scalars for the PlonK items (kzg.rs:149-154); None draws them from os.urandom."""
+    groups = {}
+    for pos, (kind, proof, vk, inputs) in enumerate(items):
+        if kind not in ("groth16", "plonk"):
+            raise ValueError("kind must be 'groth16' or 'plonk'")
+        vk = bytes(vk)
+        groups.setdefault((kind, hashlib.sha256(vk).digest(), len(inputs)), [vk, []])[1].append(pos)
+    out = np.full(len(items), STATUS_UNSET, dtype=np.uint8)
+    for (kind, _, _), (vk, positions) in groups.items():
+        proofs = [items[p][1] for p in positions]
+        inputs = [list(items[p][3]) for p in positions]
+        if kind == "groth16":
+            st = Groth16Verifier.verify_batch(proofs, vk, inputs)
+        else:
+            r = None if rnd is None else [rnd[p] for p in positions]
+            st = PlonkVerifier.verify_batch(proofs, vk, inputs, rnd=r)
+        out[np.asarray(positions)] = st
+    return out

@@ -106,3 +106,27 @@ def test_full_size_batch_config3(gpu):
     assert (status == expected).all()
     assert int((status == gpu.OK_TRUE).sum()) == n // 2
     assert {int(s) for s in np.unique(status)} == {0, 6, 8}
+
+
+def test_mixed_batch_over_several_vks(gpu):
+    """verify_many: Groth16 proofs under two different VKs (reference and gnark sign conventions are the same wire
+    format; here two trapdoor VKs) interleaved with PlonK proofs; statuses return in input order."""
+    vk_p = plonk_vk_bytes()
+    items, want = [], []
+    tds = [bo.Groth16Trapdoor(21, 2, 0), bo.Groth16Trapdoor(22, 2, 0)]
+    vks = [td.vk_bytes() for td in tds]
+    muts = [m for m in load_json("plonk_mutations.json") if m["program"] == "tendermint"][:6]
+    for i in range(6):
+        for t, td in enumerate(tds):
+            pb, xs, valid = td.proof(i)
+            items.append(("groth16", pb, vks[t], xs))
+            want.append(0 if valid else 1)
+        m = muts[i]
+        items.append(("plonk", bytes.fromhex(m["raw_proof"]), vk_p, [int(s) for s in m["inputs"]]))
+        want.append(PLONK_STATUS[m["status"]])
+    # a proof checked under the other VK is rejected
+    pb, xs, _ = tds[0].proof(0, corrupt=False)
+    items.append(("groth16", pb, vks[1], xs))
+    want.append(1)
+    st = gpu.verify_many(items)
+    assert st.tolist() == want
