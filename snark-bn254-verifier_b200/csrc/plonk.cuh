@@ -94,20 +94,98 @@ HD uint32_t be32_at(const uint8_t* b) {
   return ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
 }
 
-// [k] P for a proof-supplied point: fixed 4-bit windows over a 15-entry table (uniform control flow across the
-// threads of a warp, unlike bit-by-bit double-and-add).  k: plain 8 x u32 LE.  Same group element as the reference's
-// AffineG1 * Fr; AffineG1::msm is a plain sum of such terms.
+// ---- GLV: the curve y^2 = x^3 + 3 has the endomorphism phi(x, y) = (beta x, y) = [lambda](x, y).  A scalar splits as
+// k = k1 + k2 lambda (mod r) with |k1|, |k2| < 2^128, so [k]P = [k1]P + [k2]phi(P) needs half the doublings.
+// c1 = (k g1) >> 256, c2 = (k g2) >> 256 (rounded-down lattice coordinates; any integers give an exact identity, these
+// keep k1, k2 short), k1 = k - c1 a1 - c2 a2, k2 = -c1 b1 - c2 b2, all modulo 2^256 in two's complement.
+HD void glv_mul_hi(uint32_t* c /*5*/, const uint32_t* k /*8*/, const uint32_t* g, int g_limbs) {
+  uint32_t t[14];
+  for (int i = 0; i < 14; i++) t[i] = 0;
+  for (int j = 0; j < g_limbs; j++) {
+    uint64_t carry = 0;
+    const uint32_t gj = g[j];
+    for (int i = 0; i < 8; i++) {
+      uint64_t x = (uint64_t)k[i] * gj + t[i + j] + carry;
+      t[i + j] = (uint32_t)x;
+      carry = x >> 32;
+    }
+    t[8 + j] = (uint32_t)carry;
+  }
+  for (int i = 0; i < 5; i++) c[i] = t[8 + i];
+}
+// acc (8 limbs) += c (5 limbs) * m (8 limbs)  mod 2^256
+HD void glv_mac_lo(uint32_t* acc, const uint32_t* c, const uint32_t* m) {
+  for (int j = 0; j < 5; j++) {
+    uint64_t carry = 0;
+    for (int i = 0; i + j < 8; i++) {
+      uint64_t x = (uint64_t)m[i] * c[j] + acc[i + j] + carry;
+      acc[i + j] = (uint32_t)x;
+      carry = x >> 32;
+    }
+  }
+}
+HD bool glv_abs(uint32_t* v) {  // two's complement -> magnitude; returns the sign
+  const bool neg = (v[7] >> 31) != 0;
+  if (neg) {
+    uint64_t carry = 1;
+    for (int i = 0; i < 8; i++) {
+      uint64_t x = (uint64_t)(~v[i]) + carry;
+      v[i] = (uint32_t)x;
+      carry = x >> 32;
+    }
+  }
+  return neg;
+}
+#define BN_GLV_CONST(name, fn)          \
+  uint32_t name[8];                     \
+  _Pragma("unroll") for (int _i = 0; _i < 8; _i++) name[_i] = fn(_i);
+
+// [k] P for a proof-supplied point: GLV split, then fixed 4-bit windows for both halves over one 15-entry table
+// (phi of a table entry is one multiplication by beta) with shared doublings: 132 doublings + at most 66 additions
+// instead of 252 + 64; uniform control flow across a warp apart from zero digits.  k: plain 8 x u32 LE (< r).
+// Same group element as the reference's AffineG1 * Fr; AffineG1::msm is a plain sum of such terms.
 HDN G1Jac g1_mul_w4(const G1Aff& p, const uint32_t* k) {
+  uint32_t c1[5], c2[5], k1[8], k2[8];
+  {
+    BN_GLV_CONST(g1, K::glv_g1)
+    BN_GLV_CONST(g2, K::glv_g2)
+    glv_mul_hi(c1, k, g1, 3);
+    glv_mul_hi(c2, k, g2, 5);
+  }
+  for (int i = 0; i < 8; i++) k1[i] = k[i], k2[i] = 0;
+  {
+    BN_GLV_CONST(na1, K::glv_neg_a1)
+    BN_GLV_CONST(na2, K::glv_neg_a2)
+    BN_GLV_CONST(nb1, K::glv_neg_b1)
+    BN_GLV_CONST(nb2, K::glv_neg_b2)
+    glv_mac_lo(k1, c1, na1);
+    glv_mac_lo(k1, c2, na2);
+    glv_mac_lo(k2, c1, nb1);
+    glv_mac_lo(k2, c2, nb2);
+  }
+  const bool n1 = glv_abs(k1), n2 = glv_abs(k2);
+  Fp beta;
+  BN_LOAD_FP(beta, K::glv_beta, 0);
   G1Jac tab[15];
   tab[0] = to_jac(p);
   tab[1] = jac_double(tab[0]);
   for (int i = 2; i < 15; i++) tab[i] = jac_add_mixed(tab[i - 1], p);
   G1Jac acc = jac_identity<Fp>();
-  for (int w = 63; w >= 0; w--) {
-    if (w != 63)
+  for (int w = 32; w >= 0; w--) {  // 33 nibbles = 132 bits >= |k1|, |k2|
+    if (w != 32)
       for (int j = 0; j < 4; j++) acc = jac_double(acc);
-    uint32_t d = (k[w >> 3] >> (4 * (w & 7))) & 15;
-    if (d) acc = jac_add(acc, tab[d - 1]);
+    uint32_t d1 = (k1[w >> 3] >> (4 * (w & 7))) & 15, d2 = (k2[w >> 3] >> (4 * (w & 7))) & 15;
+    if (d1) {
+      G1Jac t = tab[d1 - 1];
+      if (n1) t.y = fe_neg(t.y);
+      acc = jac_add(acc, t);
+    }
+    if (d2) {
+      G1Jac t = tab[d2 - 1];
+      t.x = fe_mul(t.x, beta);
+      if (n2) t.y = fe_neg(t.y);
+      acc = jac_add(acc, t);
+    }
   }
   return acc;
 }

@@ -193,6 +193,16 @@ unsigned long long hs_mul_count(int reset) {  // limb multiply-adds since the la
   return 0;
 #endif
 }
+// [k] P through the GLV / windowed path of the PlonK term kernels (k: 32 bytes BE, < r); 0 on identity
+int hs_g1_mul_w4(uint8_t* out64, const uint8_t* pt64, const uint8_t* k_be) {
+  G1Aff p, r;
+  load_g1_unchecked(p, pt64);
+  Fr k;
+  fe_from_be_bytes(k, k_be);
+  if (!to_affine(r, g1_mul_w4(p, k.v))) return 0;
+  store_g1(out64, r);
+  return 1;
+}
 void hs_sha256(const uint8_t* data, uint32_t len, uint8_t* out) {
   Sha256 s;
   sha256_init(s);

@@ -231,3 +231,22 @@ def test_g2_subgroup_tests_agree(hs):
         tors = bo.g2_mul_raw(pt, bo.R)
         if tors is not None:
             assert hs.hs_g2_subgroup_both(bo.g2_to_bytes(tors)) == 0
+
+
+def test_glv_windowed_scalar_multiplication(hs):
+    """The GLV + 4-bit-window scalar multiplication of the PlonK term kernels against the oracle's double-and-add."""
+    import random
+    rng = random.Random(11)
+    pts = [bo.G1_GEN, bo.g1_mul(bo.G1_GEN, 0xABCDEF1234567), bo.g1_mul(bo.G1_GEN, bo.R - 5)]
+    lam = 0xb3c4d79d41a917585bfc41088d8daaa78b17ea66b99c90dd
+    ks = [0, 1, 2, 15, 16, bo.R - 1, bo.R - 2, lam, lam - 1, lam + 1, (lam * lam) % bo.R, bo.R // 2, 1 << 127, (1 << 128) - 1,
+          1 << 128, (1 << 253)] + [rng.randrange(bo.R) for _ in range(60)]
+    out = ctypes.create_string_buffer(64)
+    for pt in pts:
+        for k in ks:
+            ok = hs.hs_g1_mul_w4(out, bo.g1_to_bytes(pt), k.to_bytes(32, "big"))
+            want = bo.g1_mul(pt, k)
+            if want is None:
+                assert ok == 0
+            else:
+                assert ok == 1 and out.raw == bo.g1_to_bytes(want), hex(k)
