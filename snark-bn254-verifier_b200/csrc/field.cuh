@@ -197,11 +197,13 @@ HD Fe<C> fe_sub(const Fe<C>& a, const Fe<C>& b) {
   r.v[0] = cc::sub_cc(a.v[0], b.v[0]);
 #pragma unroll
   for (int i = 1; i < 8; i++) r.v[i] = cc::subc_cc(a.v[i], b.v[i]);
-  uint32_t borrow = cc::subc(0, 0);
-  r.v[0] = cc::add_cc(r.v[0], C::mod(0) & borrow);
+  const uint32_t borrow = cc::subc(0, 0);
+  if (borrow) {  // ptxas predicates these eight adds (16 instructions in all, against 25 with a masked add-back)
+    r.v[0] = cc::add_cc(r.v[0], C::mod(0));
 #pragma unroll
-  for (int i = 1; i < 7; i++) r.v[i] = cc::addc_cc(r.v[i], C::mod(i) & borrow);
-  r.v[7] = cc::addc(r.v[7], C::mod(7) & borrow);
+    for (int i = 1; i < 7; i++) r.v[i] = cc::addc_cc(r.v[i], C::mod(i));
+    r.v[7] = cc::addc(r.v[7], C::mod(7));
+  }
   return r;
 }
 
@@ -452,13 +454,13 @@ HD uint32_t wide_sub(uint32_t* X, const uint32_t* Y) {
   for (int k = 1; k < 16; k++) X[k] = cc::subc_cc(X[k], Y[k]);
   return cc::subc(0u, 0u);
 }
-// X += (m << 256) & mask   (wraps modulo 2^512: cancels the borrow of a preceding wide_sub)
+// X += m << 256   (wraps modulo 2^512: cancels the borrow of a preceding wide_sub; call under `if (borrow)`)
 template <class C>
-HD void wide_add_mod_hi(uint32_t* X, uint32_t mask) {
-  X[8] = cc::add_cc(X[8], C::mod(0) & mask);
+HD void wide_add_mod_hi(uint32_t* X) {
+  X[8] = cc::add_cc(X[8], C::mod(0));
 #pragma unroll
-  for (int k = 1; k < 7; k++) X[8 + k] = cc::addc_cc(X[8 + k], C::mod(k) & mask);
-  X[15] = cc::addc(X[15], C::mod(7) & mask);
+  for (int k = 1; k < 7; k++) X[8 + k] = cc::addc_cc(X[8 + k], C::mod(k));
+  X[15] = cc::addc(X[15], C::mod(7));
 }
 
 template <class C>

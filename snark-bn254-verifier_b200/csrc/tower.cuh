@@ -64,8 +64,7 @@ HDN Fp2 mul(Fp2 a, Fp2 b) {
   wide_sub(S, T1);
   Fp2 r;
   r.c1 = fe_redc_wide<FpCfg>(S);
-  uint32_t bw = wide_sub(T0, T1);
-  wide_add_mod_hi<FpCfg>(T0, bw);
+  if (wide_sub(T0, T1)) wide_add_mod_hi<FpCfg>(T0);  // predicated by ptxas
   r.c0 = fe_redc_wide<FpCfg>(T0);
   return r;
 }
