@@ -102,18 +102,21 @@ HD int groth16_miller_one(Fp12& f, const Groth16VkDev& vk, const uint8_t* proof,
   G2Aff B;
   int st = load_g1_checked(A, proof);
   if (st != BN254V_OK_TRUE) return st;
-  st = load_g2_checked(B, proof + 64);
+  st = load_g2_on_curve(B, proof + 64);
   if (st != BN254V_OK_TRUE) return st;
-  st = load_g1_checked(C, proof + 192);
-  if (st != BN254V_OK_TRUE) return st;
-
+  // B's subgroup test (the last check of AffineG2::new) is read off the end point of the Miller loop below.  The
+  // reference parses B before C and before the public inputs, so on a later failure B's verdict still comes first
+  // (rare path, separate scalar multiplication, no barriers).
   G1Aff L;
-  st = groth16_prepare_inputs(L, vk, inputs_be, n_inputs);
-  if (st != BN254V_OK_TRUE) return st;
-  if (dbg.L) store_g1(dbg.L, L);
+  st = load_g1_checked(C, proof + 192);
+  if (st == BN254V_OK_TRUE) st = groth16_prepare_inputs(L, vk, inputs_be, n_inputs);
+  if (st != BN254V_OK_TRUE) return g2_in_subgroup<false>(B) ? st : BN254V_PANIC_NOT_IN_SUBGROUP;
 
   G1Aff pf[2] = {L, C};
-  miller_loop_pairtab<1>(f, &A, &B, pf, vk.gd_pairs);
+  bool in_g2;
+  miller_loop_pairtab<1>(f, &A, &B, pf, vk.gd_pairs, &in_g2);
+  if (!in_g2) return BN254V_PANIC_NOT_IN_SUBGROUP;
+  if (dbg.L) store_g1(dbg.L, L);
   if (dbg.miller) fp12_to_bytes(dbg.miller, f);
   return BN254V_OK_TRUE;
 }

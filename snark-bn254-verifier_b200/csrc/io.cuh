@@ -38,14 +38,21 @@ HD void load_g2_unchecked(G2Aff& q, const uint8_t* b) {
   fp_load_be(q.y.c1, b + 64);
   fp_load_be(q.y.c0, b + 96);
 }
-HD int load_g2_checked(G2Aff& q, const uint8_t* b) {
+// AffineG2::new without its subgroup test: field membership and the curve equation only.  The Groth16 path gets the
+// subgroup verdict from the end point of the Miller loop (pairing_body.inc, ate_endpoint_in_g2).
+HD int load_g2_on_curve(G2Aff& q, const uint8_t* b) {
   bool ok = fp_load_be(q.x.c1, b);
   ok = fp_load_be(q.x.c0, b + 32) && ok;
   ok = fp_load_be(q.y.c1, b + 64) && ok;
   ok = fp_load_be(q.y.c0, b + 96) && ok;
   if (!ok) return BN254V_PANIC_FIELD_NOT_MEMBER;
   if (!on_curve(q)) return BN254V_PANIC_NOT_ON_CURVE;
-  if (!g2_in_subgroup(q)) return BN254V_PANIC_NOT_IN_SUBGROUP;
+  return BN254V_OK_TRUE;
+}
+HD int load_g2_checked(G2Aff& q, const uint8_t* b) {
+  int st = load_g2_on_curve(q, b);
+  if (st != BN254V_OK_TRUE) return st;
+  if (!g2_in_subgroup<false>(q)) return BN254V_PANIC_NOT_IN_SUBGROUP;
   return BN254V_OK_TRUE;
 }
 HD void store_g1(uint8_t* b, const G1Aff& p) {

@@ -33,6 +33,13 @@ def groth16_malformed_suite(td, index=0):
     b = bytearray(pb); b[255] ^= 2; out.append(("C off curve", bytes(b), xs, "PANIC_NOT_ON_CURVE"))
     b = bytearray(pb); b[191] ^= 1; out.append(("B off curve", bytes(b), xs, "PANIC_NOT_ON_CURVE"))
     b = bytearray(pb); b[64:192] = bo.g2_to_bytes(g2_point_outside_subgroup()); out.append(("B not in G2", bytes(b), xs, "PANIC_NOT_IN_SUBGROUP"))
+    # B is parsed before C and before prepare_inputs: its subgroup failure is the one reported
+    b = bytearray(pb); b[64:192] = bo.g2_to_bytes(g2_point_outside_subgroup(6)); b[255] ^= 2
+    out.append(("B not in G2 + C off curve", bytes(b), xs, "PANIC_NOT_IN_SUBGROUP"))
+    b[255] ^= 2
+    out.append(("B not in G2 + x0 == 0", bytes(b), [0, xs[1]], "PANIC_NOT_IN_SUBGROUP"))
+    b = bytearray(pb); b[63] ^= 1; b[64:192] = bo.g2_to_bytes(g2_point_outside_subgroup(7))
+    out.append(("A off curve + B not in G2", bytes(b), xs, "PANIC_NOT_ON_CURVE"))
     out.append(("short", pb[:255], xs, "PANIC_SHORT_BUFFER"))
     out.append(("x0 == 0", pb, [0, xs[1]], "PANIC_IDENTITY"))
     # x >= r cannot be expressed as a bn::Fr: the reference's caller fails in Fr::from_slice before verify().

@@ -54,11 +54,12 @@ int hs_g2_check(const uint8_t* g2) {
   G2Aff q;
   return load_g2_checked(q, g2);
 }
-// both subgroup predicates on an (unchecked) G2 point: bit 0 = fast test, bit 1 = 6x^2 test
+// the three subgroup predicates on an (unchecked) G2 point: bit 0 = 63-bit test, bit 1 = 6x^2 test, bit 2 = end point
+// of the Miller loop's point chain
 int hs_g2_subgroup_both(const uint8_t* g2) {
   G2Aff q;
   load_g2_unchecked(q, g2);
-  return (g2_in_subgroup(q) ? 1 : 0) | (g2_in_subgroup_6x2(q) ? 2 : 0);
+  return (g2_in_subgroup<false>(q) ? 1 : 0) | (g2_in_subgroup_6x2(q) ? 2 : 0) | (g2_in_subgroup_ate(q) ? 4 : 0);
 }
 int hs_g1_check(const uint8_t* g1) {
   G1Aff p;

@@ -215,12 +215,26 @@ def test_plonk_mutations_and_structural_cases(hs):
 
 
 def test_g2_subgroup_tests_agree(hs):
-    """The 63-bit subgroup test and the 127-bit one agree with the oracle's [r]P == 0 on subgroup points, on random
-    points of E'(Fq2) outside the subgroup, and on points of the form (subgroup point + cofactor-torsion point)."""
+    """The 63-bit subgroup test, the 127-bit one and the Miller-loop end-point test agree with the oracle's [r]P == 0
+    on subgroup points, on random points of E'(Fq2) outside the subgroup, on points of the form (subgroup point +
+    cofactor-torsion point) and on points of the small order 10069 (where the step formulas can hit their
+    exceptional cases)."""
     from helpers import g2_point_outside_subgroup
     for k in (1, 2, 12345, bo.R - 1):
         pt = bo.g2_mul(bo.G2_GEN, k)
-        assert hs.hs_g2_subgroup_both(bo.g2_to_bytes(pt)) == 3
+        assert hs.hs_g2_subgroup_both(bo.g2_to_bytes(pt)) == 7
+    h2 = 2 * bo.P - bo.R
+    assert h2 % 10069 == 0
+    for seed in (5, 6, 7):
+        small = bo.g2_mul_raw(g2_point_outside_subgroup(seed), bo.R * (h2 // 10069))
+        if small is None:
+            continue
+        assert bo.g2_mul_raw(small, 10069) is None
+        for k in (1, 2, 3, 5034, 5035, 10068):
+            pt = bo.g2_mul_raw(small, k)
+            assert hs.hs_g2_subgroup_both(bo.g2_to_bytes(pt)) == 0
+            mixed = bo.g2_add(pt, bo.g2_mul(bo.G2_GEN, 77 + seed))
+            assert hs.hs_g2_subgroup_both(bo.g2_to_bytes(mixed)) == 0
     for seed in (5, 6, 7, 100, 1000):
         pt = g2_point_outside_subgroup(seed)
         assert not bo.g2_in_subgroup(pt)

@@ -179,3 +179,24 @@ def test_groth16_error_and_panic_classes():
     with pytest.raises(bo.PanicError) as e:
         bo.groth16_verifier_verify(pb, vk, [0, xs[1]])
     assert e.value.kind == "IDENTITY"
+
+
+def test_ate_endpoint_subgroup_test_is_exact():
+    """The integers behind pairing_body.inc's ate_endpoint_in_g2: 6x+2 + p - p^2 + p^3 = 0 (mod r), and the norm of
+    phi = 6x+2 + psi - psi^2 + psi^3 in Z[psi] (psi^2 - t psi + p = 0) shares exactly the factor r with #E'(Fq2) =
+    r (2p - r), so phi(Q) = O <=> ord(Q) | r on E'(Fq2).  Same computation for the 63-bit test of curve_body.inc."""
+    from math import gcd
+    x = 4965661367192848881
+    p, r = bo.P, bo.R
+    assert p == 36 * x**4 + 36 * x**3 + 24 * x**2 + 6 * x + 1 and r == p - 6 * x * x
+    t = 6 * x * x + 1
+    assert (6 * x + 2 + p - p * p + p**3) % r == 0
+    n_curve = r * (2 * p - r)
+
+    def norm(c0, c1, c2, c3):  # N(c0 + c1 X + c2 X^2 + c3 X^3) modulo X^2 - tX + p
+        a = c1 + c2 * t + c3 * (t * t - p)
+        b = c0 - c2 * p - c3 * t * p
+        return a * a * p + a * b * t + b * b
+
+    assert gcd(norm(6 * x + 2, 1, -1, 1), n_curve) == r
+    assert gcd(norm(x + 1, x, x, -2 * x), n_curve) == r
