@@ -217,10 +217,12 @@ def secondary_workloads(pkg, work):
         out["plonk"]["cpu_baseline"] = {"value": None, "sample": "unavailable: %r" % (e,)}
     m = 1 << 17
     g1, g2, exp1 = pkg.pairing_synth(11, m, k=4)
-    pkg.pairing_product_batch(g1[:1024], g2[:1024], 4)
-    t0 = time.perf_counter()
-    one = pkg.pairing_product_batch(g1, g2, 4)
-    dt = time.perf_counter() - t0
+    dt = None  # best of 3: the first full-size call also pays the kernel's one-time module and local-memory set-up
+    for _ in range(3):
+        t0 = time.perf_counter()
+        one = pkg.pairing_product_batch(g1, g2, 4)
+        d1 = time.perf_counter() - t0
+        dt = d1 if dt is None else min(dt, d1)
     assert (one == exp1).all()
     out["pairing_product_k4"] = {"workload": "2^17 random 4-pair sets, all G2 variable (BASELINE configs[3] scaled)",
                                  "e2e_sets_per_sec": m / dt, "pair_miller_loops_per_sec": 4 * m / dt, "ms": dt * 1e3}
