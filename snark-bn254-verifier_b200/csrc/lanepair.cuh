@@ -95,6 +95,7 @@ HDN Fp2 sqr(Fp2 a) {
   return Fp2{fe_mul(X, Y)};
 }
 HD Fp2 scale(const Fp2& a, const Fp& k) { return Fp2{fe_mul(a.c, k)}; }
+HD Fp2 scale2_add(const Fp2& a, const Fp& j, const Fp2& b, const Fp& k) { return Fp2{fe_mul2_add(a.c, j, b.c, k)}; }
 // (9 + u)(a0 + a1 u) = (9 a0 - a1) + (9 a1 + a0) u
 HDN Fp2 mul_xi(Fp2 a) {
   Fp oa = xchg(a.c);

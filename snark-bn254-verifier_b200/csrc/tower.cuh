@@ -75,6 +75,10 @@ HDN Fp2 sqr(Fp2 a) {
   return Fp2{c0, c1};
 }
 HD Fp2 scale(const Fp2& a, const Fp& k) { return Fp2{fe_mul(a.c0, k), fe_mul(a.c1, k)}; }
+// a j + b k for Fq scalars j, k (one reduction per component)
+HD Fp2 scale2_add(const Fp2& a, const Fp& j, const Fp2& b, const Fp& k) {
+  return Fp2{fe_mul2_add(a.c0, j, b.c0, k), fe_mul2_add(a.c1, j, b.c1, k)};
+}
 // multiply by xi = 9 + u: (9 a0 - a1) + (a0 + 9 a1) u
 HDN Fp2 mul_xi(Fp2 a) {
   return Fp2{fe_mul9_add(a.c0, fe_mod_minus(a.c1)), fe_mul9_add(a.c1, a.c0)};
