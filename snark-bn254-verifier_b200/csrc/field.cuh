@@ -123,7 +123,7 @@ struct FrCfg {  // scalar field, r
 };
 
 template <class C>
-struct Fe {
+struct alignas(16) Fe {
   uint32_t v[8];
 };
 
@@ -479,6 +479,81 @@ HDN Fe<C> fe_mul2_add(Fe<C> a, Fe<C> b, Fe<C> c, Fe<C> d) {
   fe_mul_wide(T1, c, d);
   wide_add(T0, T1);
   return fe_redc_wide<C>(T0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Signed 512-bit values (two's complement, 16 words) for lazy reduction one level up (Fq6): sums and differences of
+// unreduced products are formed with wide_add / wide_sub and reduced once per output coefficient.
+// ---------------------------------------------------------------------------------------------
+// Montgomery reduction of a signed wide value V, -m 2^256 < V < K m 2^256 (K = 1, or 2 with TWICE): V / 2^256 mod m,
+// fully reduced.  A negative V gets m 2^256 added first (same residue); fe_redc_wide's U + T_hi is then < (K + 1) m.
+template <class C, bool TWICE>
+HD Fe<C> fe_redc_wide_signed(uint32_t* T) {
+  if (T[15] >> 31) wide_add_mod_hi<C>(T);
+  Fe<C> r = fe_redc_wide<C>(T);
+  if (TWICE) fe_reduce_once<C>(r.v);
+  return r;
+}
+
+// Z = 9 X + Y (SUB = false) or 9 X - Y (SUB = true) modulo m 2^256, as a signed value with |Z| <= (1/2 + 1e-4) m 2^256.
+// X, Y signed wide values with -4.2 m 2^256 < 9 X +- Y < 7.2 m 2^256 (the two uses in the Fq6 multiplication).
+// The 17-word sum A gets 5 m 2^256 added (A' > 0), q = round(A' / (m 2^256)) is estimated from the top 26 bits of A'
+// (a' = A' >> 488, q = (a' * 43337 + 2^36) >> 37: m / 2^232 = 3171406.45 and 2^37 / 3171406.45 = 43336.9, so the
+// estimate is off by < 1e-4 before rounding), and q m is subtracted from the high half.  BN254 base field only.
+template <class C, bool SUB>
+HD void wide_mul9_addsub(uint32_t* Z, const uint32_t* X, const uint32_t* Y) {
+  constexpr uint32_t FIVE_M[8] = {0x3a70f263u, 0x2ca2bc72u, 0x0a38f4c2u, 0xf58714d7u,
+                                  0x8786b9d3u, 0x99915c90u, 0x65f820d0u, 0xf1f5883eu};
+  uint32_t t[17];
+  const uint32_t nx = X[15] >> 31, ny = Y[15] >> 31;
+  if (SUB) {
+    t[0] = X[0] * 9u;
+    t[1] = cc::mad_hi_cc(X[0], 9u, 0u);
+#pragma unroll
+    for (int i = 1; i < 15; i++) t[i + 1] = cc::madc_hi_cc(X[i], 9u, 0u);
+    t[16] = cc::madc_hi(X[15], 9u, 0u);
+    t[1] = cc::mad_lo_cc(X[1], 9u, t[1]);
+#pragma unroll
+    for (int i = 2; i < 16; i++) t[i] = cc::madc_lo_cc(X[i], 9u, t[i]);
+    t[16] = cc::addc(t[16], 0u);
+    t[0] = cc::sub_cc(t[0], Y[0]);
+#pragma unroll
+    for (int i = 1; i < 16; i++) t[i] = cc::subc_cc(t[i], Y[i]);
+    t[16] = cc::subc(t[16], 0u);
+    t[16] = t[16] - 9u * nx + ny;  // sign extensions of X and Y (unsigned words stood for value + 2^512)
+  } else {
+    t[0] = cc::mad_lo_cc(X[0], 9u, Y[0]);
+#pragma unroll
+    for (int i = 1; i < 16; i++) t[i] = cc::madc_lo_cc(X[i], 9u, Y[i]);
+    t[16] = cc::addc(0u, 0u);
+    t[1] = cc::mad_hi_cc(X[0], 9u, t[1]);
+#pragma unroll
+    for (int i = 1; i < 15; i++) t[i + 1] = cc::madc_hi_cc(X[i], 9u, t[i + 1]);
+    t[16] = cc::madc_hi(X[15], 9u, t[16]);
+    t[16] = t[16] - 9u * nx - ny;
+  }
+  // A' = A + 5 m 2^256
+  t[8] = cc::add_cc(t[8], FIVE_M[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) t[8 + i] = cc::addc_cc(t[8 + i], FIVE_M[i]);
+  t[16] = cc::addc(t[16], 0u);
+  const uint32_t ap = (t[16] << 24) | (t[15] >> 8);
+  const uint32_t q = (uint32_t)(((uint64_t)ap * 43337u + (1ull << 36)) >> 37);
+  uint32_t u[9];
+  u[0] = cc::mad_lo_cc(C::mod(0), q, 0u);
+#pragma unroll
+  for (int i = 1; i < 8; i++) u[i] = cc::madc_lo_cc(C::mod(i), q, 0u);
+  u[8] = cc::addc(0u, 0u);
+  u[1] = cc::mad_hi_cc(C::mod(0), q, u[1]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) u[i + 1] = cc::madc_hi_cc(C::mod(i), q, u[i + 1]);
+  u[8] = cc::madc_hi(C::mod(7), q, u[8]);
+#pragma unroll
+  for (int i = 0; i < 8; i++) Z[i] = t[i];
+  Z[8] = cc::sub_cc(t[8], u[0]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) Z[8 + i] = cc::subc_cc(t[8 + i], u[i]);
+  Z[15] = cc::subc(t[15], u[7]);  // word 16 (t[16] - u[8] - borrow) is the sign extension of word 15
 }
 
 template <class C>

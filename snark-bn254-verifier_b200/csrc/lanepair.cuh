@@ -123,6 +123,7 @@ HD Fp2 frob_coeff(int i) {
 template <int KK>
 HD Fp frob_coeff_fp(int i) { return bn254::frob_coeff<KK>(i).c0; }
 
+#undef BN_HAVE_FP6_MUL_LAZY  // the lazily reduced Fq6 multiplication is written for the scalar Fq2 layout
 #include "tower_body.inc"
 
 HD Fp12 ld12(const Fp12F& s) {

@@ -89,6 +89,83 @@ HD Fp2 inv(const Fp2& a) {
 }
 HD Fp2 fp2_halve(const Fp2& a) { return Fp2{fe_halve(a.c0), fe_halve(a.c1)}; }
 
+// ---- unreduced Fq2 values for the lazily reduced Fq6 multiplication (tower_body.inc, mul_lazy; an experiment that is
+// bit-exact and has 21 % fewer multiply-adds per Fq6 multiplication but measured 11 % slower per Groth16 batch on B200
+// than the plain Karatsuba below -- see DESIGN.md section 6 -- so it is opt-in: -DBN_FP6_MUL_LAZY).
+// A Wide2 holds re + im u as two signed 512-bit integers (Montgomery scale 2^256 not yet divided out).  In units of
+// p^2 (p 2^256 = 5.29 p^2, signed 512-bit range +-13.9 p^2): a product of reduced operands has re in (-1, 1) and
+// im in [0, 2).
+struct alignas(16) Wide {
+  uint32_t v[16];
+};
+struct Wide2 {
+  Wide re, im;
+};
+// Karatsuba, 3 full products, no reduction: re = a0 b0 - a1 b1, im = (a0 + a1)(b0 + b1) - a0 b0 - a1 b1
+HD void mul_wide_inl(Wide2& r, const Fp2& a, const Fp2& b) {
+  uint32_t T1[16];
+  fe_mul_wide(r.re.v, a.c0, b.c0);
+  fe_mul_wide(T1, a.c1, b.c1);
+  fe_mul_wide(r.im.v, fe_add_nr(a.c0, a.c1), fe_add_nr(b.c0, b.c1));
+  wide_sub(r.im.v, r.re.v);
+  wide_sub(r.im.v, T1);
+  wide_sub(r.re.v, T1);
+}
+HDN void mul_wide(Wide2& r, Fp2 a, Fp2 b) {
+  Wide2 t;
+  mul_wide_inl(t, a, b);
+  r = t;  // whole-struct copy: 128-bit local stores
+}
+// x +- y with y copied to registers half by half as a whole struct (128-bit local loads; element-wise reads between
+// the carry-chain asm statements are not merged by the compiler)
+HD void wadd(Wide2& x, const Wide2& y) {
+  {
+    const Wide t = y.re;
+    wide_add(x.re.v, t.v);
+  }
+  const Wide t = y.im;
+  wide_add(x.im.v, t.v);
+}
+HD void wsub(Wide2& x, const Wide2& y) {
+  {
+    const Wide t = y.re;
+    wide_sub(x.re.v, t.v);
+  }
+  const Wide t = y.im;
+  wide_sub(x.im.v, t.v);
+}
+// x <- xi x = (9 re - im) + (9 im + re) u, each component brought back to |.| <= 2.65 p^2 modulo p 2^256.
+// Valid for re in (-2, 2), im in [0, 4) (p^2 units): 9 re - im in (-22, 18), 9 im + re in (-2, 38).
+HD void mul_xi_wide_inl(Wide2& x) {
+  Wide t;
+  wide_mul9_addsub<FpCfg, true>(t.v, x.re.v, x.im.v);
+  wide_mul9_addsub<FpCfg, false>(x.im.v, x.im.v, x.re.v);
+  x.re = t;
+}
+HDN void mul_xi_wide(Wide2& x) {
+  Wide2 t = x;
+  mul_xi_wide_inl(t);
+  x = t;
+}
+// One output coefficient of the lazily reduced Fq6 multiplication: (XI ? xi : 1)(a b - X - Y) + Z, reduced.  The running
+// value stays in registers from the products to the reductions; X, Y, Z stream in from local memory once.
+// Ranges (p^2 units): a b - X - Y has re in (-2, 2), im in [0, 4) when XI; the final value has re in (-5.29, 5.29) and
+// im in (-5.29, 5.29), or im in (-5.29, 10.58) with TWICE.
+template <bool XI, bool TWICE>
+HDN Fp2 mul_sub2_add(Fp2 a, Fp2 b, const Wide2& X, const Wide2& Y, const Wide2& Z) {
+  Wide2 P;
+  mul_wide_inl(P, a, b);
+  wsub(P, X);
+  wsub(P, Y);
+  if (XI) mul_xi_wide_inl(P);
+  wadd(P, Z);
+  Fp2 r;
+  r.c0 = fe_redc_wide_signed<FpCfg, false>(P.re.v);
+  r.c1 = fe_redc_wide_signed<FpCfg, TWICE>(P.im.v);
+  return r;
+}
+#define BN_HAVE_FP6_MUL_LAZY  // tower_body.inc: mul_lazy(Fp6&, ..) is compiled; -DBN_FP6_MUL_LAZY makes it the Fq6 multiplier
+
 #define BN_LOAD_FP2(dst, fn, idx) \
   {                               \
     BN_LOAD_FP((dst).c0, fn, 2 * (idx)); \

@@ -166,6 +166,16 @@ void hs_fp2_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {  // 16 word
   Fp2 z = mul(x, y);
   memcpy(r, z.c0.v, 32), memcpy(r + 8, z.c1.v, 32);
 }
+void hs_fp6_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {  // 48 words each: c0.c0 | c0.c1 | c1.c0 | ... (Montgomery)
+  Fp6 x, y, z, zl;
+  memcpy(&x, a, 192), memcpy(&y, b, 192);
+  mul(z, x, y);
+  mul_lazy(zl, x, y);  // the opt-in lazily reduced multiplier must give the same element
+  memcpy(r, &z, 192);
+  if (memcmp(&zl, &z, 192) != 0) memset(r, 0xff, 192);
+  mul_lazy(x, x, y);  // aliased destination
+  if (memcmp(&x, &z, 192) != 0) memset(r, 0xff, 192);
+}
 void hs_fp2_mul_xi(uint32_t* r, const uint32_t* a) {
   Fp2 x;
   memcpy(x.c0.v, a, 32), memcpy(x.c1.v, a + 8, 32);

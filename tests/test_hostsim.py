@@ -74,6 +74,50 @@ def test_fp2_mul_sqr_lazy_reduction_edge_cases(hs):
         assert sum(int(h[i]) << (32 * i) for i in range(8)) == a0 * pow(2, -1, bo.P) % bo.P
 
 
+def test_fp6_mul_lazy_reduction_edge_cases(hs):
+    """The lazily reduced Fq6 multiplication (6 unreduced Fq2 products, signed 512-bit sums, multiplication by xi with
+    a reduction modulo p 2^256, 6 Montgomery reductions) against big-integer schoolbook arithmetic, on random operands
+    and on the operands that drive the intermediate sums to the ends of their ranges (all coefficients 0 / p-1)."""
+    import itertools
+    import random
+    rng = random.Random(13)
+    rinv = pow(1 << 256, -1, bo.P)
+    P = bo.P
+
+    def words(cs):
+        return (ctypes.c_uint32 * 48)(*[(c >> (32 * i)) & 0xFFFFFFFF for c in cs for i in range(8)])
+
+    def f2mul(x, y):
+        return ((x[0] * y[0] - x[1] * y[1]) % P, (x[0] * y[1] + x[1] * y[0]) % P)
+
+    def f2add(x, y):
+        return ((x[0] + y[0]) % P, (x[1] + y[1]) % P)
+
+    def xi(x):
+        return ((9 * x[0] - x[1]) % P, (9 * x[1] + x[0]) % P)
+
+    def ref(a, b):
+        A = [(a[0], a[1]), (a[2], a[3]), (a[4], a[5])]
+        B = [(b[0], b[1]), (b[2], b[3]), (b[4], b[5])]
+        c0 = f2add(f2mul(A[0], B[0]), xi(f2add(f2mul(A[1], B[2]), f2mul(A[2], B[1]))))
+        c1 = f2add(f2add(f2mul(A[0], B[1]), f2mul(A[1], B[0])), xi(f2mul(A[2], B[2])))
+        c2 = f2add(f2add(f2mul(A[0], B[2]), f2mul(A[1], B[1])), f2mul(A[2], B[0]))
+        return [v * rinv % P for c in (c0, c1, c2) for v in c]
+
+    hi, lo = P - 1, 0
+    cases = []
+    for bits in itertools.product((lo, hi), repeat=12):  # every 0 / p-1 pattern of both operands
+        cases.append((list(bits[:6]), list(bits[6:])))
+    edge = [0, 1, P - 1, P - 2, (P - 1) // 2, (P + 1) // 2, 1 << 253, (1 << 256) % P]
+    cases += [([rng.choice(edge) for _ in range(6)], [rng.choice(edge) for _ in range(6)]) for _ in range(1500)]
+    cases += [([rng.randrange(P) for _ in range(6)], [rng.randrange(P) for _ in range(6)]) for _ in range(3000)]
+    out = (ctypes.c_uint32 * 48)()
+    for a, b in cases:
+        hs.hs_fp6_mul(out, words(a), words(b))
+        got = [sum(int(out[8 * k + i]) << (32 * i) for i in range(8)) for k in range(6)]
+        assert got == ref(a, b), (a, b)
+
+
 def test_pairing_products_match_golden(hs):
     for c in load_json("pairing_golden.json"):
         ml, gt = ctypes.create_string_buffer(384), ctypes.create_string_buffer(384)
