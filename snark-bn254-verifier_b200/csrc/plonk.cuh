@@ -562,8 +562,7 @@ HD int plonk_stage_e(PlonkWork& w, const PlonkVkDev& vk, const uint8_t* pr, cons
   if (is_identity(fdg)) return BN254V_PANIC_IDENTITY;
   fq.y = neg(fq.y);
   G1Aff pf[2];
-  to_affine(pf[0], fdg);
-  to_affine(pf[1], fq);
+  to_affine2(pf[0], fdg, pf[1], fq);  // both checked non-identity above; one shared inversion
   if (dbg.g1) {
     store_g1(dbg.g1 + 128, pf[0]);
     store_g1(dbg.g1 + 192, pf[1]);

@@ -108,6 +108,17 @@ def test_full_size_batch_config3(gpu):
     assert {int(s) for s in np.unique(status)} == {0, 6, 8}
 
 
+def test_big_batch_several_chunks(gpu):
+    """150 000 proofs: three workspace chunks (2^16 proofs each at most), survivors listed per chunk; every status as
+    expected."""
+    import workloads
+    n = 150000
+    proofs, inputs, rnd, expected = workloads.plonk_workload(n, seed=5)
+    status = gpu.PlonkVerifier.verify_batch(proofs, plonk_vk_bytes(), inputs, rnd=rnd)
+    assert (status == expected).all()
+    assert {int(s) for s in np.unique(status)} == {0, 6, 8}
+
+
 def test_mixed_batch_over_several_vks(gpu):
     """verify_many: Groth16 proofs under two different VKs (reference and gnark sign conventions are the same wire
     format; here two trapdoor VKs) interleaved with PlonK proofs; statuses return in input order."""

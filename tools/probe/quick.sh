@@ -2,4 +2,4 @@
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
 timeout 300 python bench.py --steps 10 --warmup 3 2>/dev/null | tail -1 | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print('step ms', d['ms_per_step'], 'proofs/s', d['value'], 'miller', d['roofline']['kernel_ms_per_launch'], 'finish', d['roofline']['step']['finish_ms_per_launch'], 'plonk ms', d['plonk']['ms'], 'pp4 ms', d['pairing_product_k4']['ms'], 'e2e', d['e2e']['value'])"
+d=json.loads(sys.stdin.read()); print('step ms', d['ms_per_step'], 'proofs/s', d['value'], 'miller', d['roofline']['kernel_ms_per_launch'], 'finish', d['roofline']['step']['finish_ms_per_launch'], 'plonk ms', d['plonk']['ms'], 'plonk 2^17 proofs/s', d['plonk']['e2e_proofs_per_sec_2e17_batch'], 'pp4 ms', d['pairing_product_k4']['ms'], 'e2e', d['e2e']['value'])"
