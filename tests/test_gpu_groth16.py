@@ -104,6 +104,29 @@ def test_full_size_batch_properties(gpu):
     batch.free()
 
 
+def test_multi_wave_batch_with_malformed_proofs(gpu):
+    """240 000 proofs (the 384-thread / 168-register two-launch shape used from 148 x 384 x 4 proofs up), with malformed
+    records scattered through the batch: every verdict equals the generator's, every malformed record gets its own
+    status, and rejected threads leaving early do not disturb their blocks' barriers."""
+    n = 240000
+    vk, proofs, inputs, expected = gpu.groth16_synth(77, n)
+    proofs = proofs.copy(); expected = expected.copy()
+    rng = np.random.default_rng(3)
+    # off-curve A, off-curve C, B.x0 == p, on a few hundred random positions
+    pos = rng.choice(n, size=600, replace=False)
+    for j, i in enumerate(pos):
+        kind = j % 3
+        if kind == 0:
+            proofs[i, 63] ^= 1; expected[i] = gpu.PANIC_NOT_ON_CURVE
+        elif kind == 1:
+            proofs[i, 255] ^= 2; expected[i] = gpu.PANIC_NOT_ON_CURVE
+        else:
+            proofs[i, 96:128] = np.frombuffer(bo.P.to_bytes(32, "big"), dtype=np.uint8)
+            expected[i] = gpu.PANIC_FIELD_NOT_MEMBER
+    status = gpu.Groth16Verifier.verify_batch(proofs, vk, inputs)
+    assert (status == expected).all()
+
+
 def test_more_public_inputs(gpu):
     """|IC| other than 3 (prepare_inputs loops over n_public)."""
     for n_public in (1, 4):
