@@ -48,6 +48,7 @@ enum bn254v_status {
   BN254V_PANIC_SHORT_BUFFER = 20,    /* slice index out of range                groth16/converter.rs:15 */
   BN254V_PANIC_DIV_BY_ZERO = 21,     /* Fr `/=` by zero                          plonk/verify.rs:157  */
   BN254V_PANIC_INDEX_OUT_OF_RANGE = 22, /* claimed_values[1..5] missing           plonk/verify.rs:166-170 */
+  BN254V_PANIC_VK_PARSE = 23,        /* VK parser error unwrapped (verify_many items)  lib.rs:46,71       */
   BN254V_STATUS_UNSET = 255
 };
 
@@ -110,50 +111,52 @@ int bn254v_groth16_verify_batch(const bn254v_vk* vk, const uint8_t* proofs, size
                                 const uint32_t* proof_len, const uint8_t* inputs_be, int n_inputs,
                                 size_t n, uint8_t* status, const bn254v_debug* dbg);
 
-/* rnd_be: n * 32 bytes -- the scalar the reference draws from OsRng in
- * kzg::batch_verify_multi_points (verifier/src/plonk/kzg.rs:149-154); reduced mod r on device. */
+/* rnd_be: the per-proof scalar the reference draws from OsRng inside kzg::batch_verify_multi_points
+ * (verifier/src/plonk/kzg.rs:149-154).
+ *   NULL (the production path): the library draws n fresh 32-byte scalars from the operating system's CSPRNG
+ *     (getrandom(2)) for every call, redrawing any that is 0 mod r, exactly where the reference calls Fr::random.
+ *   non-NULL (tests / reproducible runs only): n * 32 bytes, reduced mod r on device.  SECURITY: the scalar separates
+ *     the two openings of the batched KZG check; if it is 0 mod r, or known to the prover before the proof is fixed
+ *     (a constant, a reused array, a seeded PRNG), the z-shifted opening Z(omega zeta) = zu is effectively unchecked
+ *     and proofs can be forged.  Never pass caller-chosen values in production. */
 int bn254v_plonk_verify_batch(const bn254v_vk* vk, const uint8_t* proofs, size_t proof_stride,
                               const uint32_t* proof_len, const uint8_t* inputs_be, int n_inputs,
                               const uint8_t* rnd_be, size_t n, uint8_t* status, const bn254v_debug* dbg);
 
 /* Raw k-pair pairing-product check (bn::pairing_batch, k <= 4): g1 n*k*64 (x|y), g2 n*k*128
- * (x1|x0|y1|y0).  Points are trusted (no validation); a pair whose G1 is all-zero bytes is skipped.
+ * (x1|x0|y1|y0).  Points are trusted (no validation: bn::pairing_batch takes group elements).  The identity is
+ * encoded as all-zero bytes (64 for G1, 128 for G2); a pair with an identity member is skipped, as
+ * substrate-bn's pairing_batch skips it (a set of skipped pairs only has Miller value 1).
  * is_one[i] = 1 iff the product of pairings is the identity of GT.                              */
 int bn254v_pairing_product_batch(const uint8_t* g1, const uint8_t* g2, int k, size_t n,
                                  uint8_t* is_one, uint8_t* miller_out, uint8_t* gt_out);
 
-/* ---- device-resident variants (inputs already in HBM; used for kernel-only timing) ------------ */
-/* Opaque staged batch: uploads once, can be verified repeatedly without host copies.            */
-typedef struct bn254v_batch bn254v_batch;
-int bn254v_groth16_batch_upload(const bn254v_vk* vk, const uint8_t* proofs, size_t proof_stride,
-                                const uint8_t* inputs_be, int n_inputs, size_t n, bn254v_batch** out);
-/* Runs the verification kernels on the staged batch; *kernel_ms (nullable) receives the device
- * time (CUDA events on the launching stream, max over devices).  status (nullable) is copied back
- * after the timed region.                                                                        */
-int bn254v_groth16_batch_verify(const bn254v_vk* vk, bn254v_batch* batch, uint8_t* status, float* kernel_ms);
-void bn254v_batch_free(bn254v_batch* batch);
+/* ---- VK cache and mixed batches ------------------------------------------------------------------
+ * The reference parses the VK on every call (verifier/src/lib.rs:46,71 -> groth16/converter.rs:28-89,
+ * plonk/converter.rs:18-119).  Here a VK costs a host decompression plus device precomputation (line tables,
+ * e(alpha,beta'), window tables), so the library keeps the handles it has built, keyed by
+ * sha256(vk bytes) -- SP1's *_vkey_hash -- kind and sign_mode.  A cached handle is owned by the library: do not
+ * pass it to bn254v_vk_free; bn254v_vk_cache_clear / bn254v_shutdown release them.                          */
+enum bn254v_kind { BN254V_KIND_GROTH16 = 0, BN254V_KIND_PLONK = 1 };
+int bn254v_vk_cache_get(int kind, const uint8_t* vk_bytes, size_t len, int sign_mode, const bn254v_vk** out);
+size_t bn254v_vk_cache_size(void);
+void bn254v_vk_cache_clear(void);
 
-/* ---- synthetic workloads (BASELINE.json configs 2 and 4; generated on device) ------------------
- * Trapdoor-simulated Groth16 instance set: writes the gnark VK bytes (*vk_len in: capacity, out:
- * length), n proofs of 256 bytes and n * n_public * 32 input bytes; 50 % of the proofs are
- * corrupted (expected[i] = BN254V_OK_TRUE or BN254V_OK_FALSE).  Same PRNG definition as the
- * oracle's generator (oracle/bn254_oracle.py Groth16Trapdoor) so both sides can be compared.     */
-int bn254v_groth16_synth(uint64_t seed, int n_public, int sign_mode, size_t first_index, size_t n,
-                         uint8_t* vk_bytes, size_t* vk_len, uint8_t* proofs, uint8_t* inputs_be,
-                         uint8_t* expected);
-/* Random k-pair sets P_j = s_j G1, Q_j = t_j G2; odd-indexed sets are solved so the product is 1. */
-int bn254v_pairing_synth(uint64_t seed, int k, size_t first_index, size_t n, uint8_t* g1, uint8_t* g2,
-                         uint8_t* expected_is_one);
-
-/* ---- measurement helpers --------------------------------------------------------------------- */
-/* Dependent-free IMAD.WIDE.U32 stream on device 0: returns achieved multiply-adds per second
- * (the int32 roofline denominator).  iters >= 1.                                 */
-int bn254v_imad_peak(int iters, double* wide_mac_per_s, double* lo_mac_per_s, float* sm_clock_mhz);
-/* Device times (CUDA events, device slot 0) of the two launches of the last bn254v_groth16_batch_verify: the Miller-loop
- * kernel and the final-exponentiation kernel (finish_ms = 0 when the batch ran as one fused launch).              */
-int bn254v_last_kernel_split(float* miller_ms, float* finish_ms);
-/* Number of kernel launches issued by this library since init (for bench.py's gpu_launches).    */
-uint64_t bn254v_launch_count(void);
+/* One item of a mixed batch: what one call of Groth16Verifier::verify / PlonkVerifier::verify receives
+ * (verifier/src/lib.rs:44,69).  Items that share (kind, vk bytes, n_inputs) are verified as one device batch. */
+typedef struct bn254v_item {
+  int kind;                 /* enum bn254v_kind                                             */
+  int n_inputs;             /* number of public inputs                                      */
+  const uint8_t* proof;     /* gnark raw proof                                              */
+  size_t proof_len;
+  const uint8_t* vk;        /* gnark VK bytes (identical pointers are recognised without hashing) */
+  size_t vk_len;
+  const uint8_t* inputs_be; /* n_inputs * 32 bytes, big-endian Fr                           */
+} bn254v_item;
+/* Verifies n items over any number of verifying keys and both proof systems; status[i] belongs to items[i].
+ * A VK that does not parse gives BN254V_PANIC_VK_PARSE for its items (the reference unwraps the VK parser).
+ * rnd_be: NULL (production) or n * 32 bytes, used by the PlonK items only (see bn254v_plonk_verify_batch).    */
+int bn254v_verify_many(const bn254v_item* items, size_t n, int sign_mode, const uint8_t* rnd_be, uint8_t* status);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,6 @@ ctypes; there is no CPU fallback and nothing here imports ``oracle/``.
 from __future__ import annotations
 
 import ctypes
-import hashlib
 import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_size_t, c_uint8, c_uint32, c_uint64, c_void_p
 
@@ -28,18 +27,24 @@ OK_TRUE, OK_FALSE = 0, 1
 ERR_PREPARE_INPUTS, ERR_BSB22_MISMATCH, ERR_INVALID_WITNESS, ERR_INVERSE_NOT_FOUND = 2, 3, 4, 5
 ERR_OPENING_POLY_MISMATCH, ERR_INVALID_NUMBER_OF_DIGESTS, ERR_PAIRING_CHECK_FAILED = 6, 7, 8
 PANIC_FIELD_NOT_MEMBER, PANIC_NOT_ON_CURVE, PANIC_NOT_IN_SUBGROUP, PANIC_IDENTITY = 16, 17, 18, 19
-PANIC_SHORT_BUFFER, PANIC_DIV_BY_ZERO, PANIC_INDEX_OUT_OF_RANGE, STATUS_UNSET = 20, 21, 22, 255
+PANIC_SHORT_BUFFER, PANIC_DIV_BY_ZERO, PANIC_INDEX_OUT_OF_RANGE, PANIC_VK_PARSE, STATUS_UNSET = 20, 21, 22, 23, 255
+KIND_GROTH16, KIND_PLONK = 0, 1
 
 E_BAD_ARG, E_NO_DEVICE, E_CUDA, E_VK_PARSE, E_UNSUPPORTED = -1, -2, -3, -4, -5
 
-# every symbol include/bn254v.h declares (tests check that the library exports them all)
+# every symbol include/bn254v.h (the verifier) and include/bn254v_bench.h (measurement / test support) declare;
+# tests check that the library exports them all
 EXPORTS = [
     "bn254v_init", "bn254v_shutdown", "bn254v_device_count", "bn254v_last_error", "bn254v_status_name",
     "bn254v_groth16_vk_load", "bn254v_plonk_vk_load", "bn254v_vk_free", "bn254v_vk_n_public",
     "bn254v_groth16_verify_batch", "bn254v_plonk_verify_batch", "bn254v_pairing_product_batch",
-    "bn254v_groth16_batch_upload", "bn254v_groth16_batch_verify", "bn254v_batch_free",
+    "bn254v_vk_cache_get", "bn254v_vk_cache_size", "bn254v_vk_cache_clear", "bn254v_verify_many",
+]
+BENCH_EXPORTS = [
+    "bn254v_groth16_batch_upload", "bn254v_groth16_batch_verify", "bn254v_plonk_batch_upload",
+    "bn254v_plonk_batch_verify", "bn254v_pairing_batch_upload", "bn254v_pairing_batch_verify", "bn254v_batch_free",
+    "bn254v_last_stage_ms", "bn254v_last_kernel_split",
     "bn254v_groth16_synth", "bn254v_pairing_synth", "bn254v_imad_peak", "bn254v_launch_count",
-    "bn254v_last_kernel_split",
 ]
 
 
@@ -77,6 +82,11 @@ class VerifierPanic(Exception):
 
 class _Debug(ctypes.Structure):
     _fields_ = [("g1_out", c_void_p), ("fr_out", c_void_p), ("miller_out", c_void_p), ("gt_out", c_void_p)]
+
+
+class _Item(ctypes.Structure):  # bn254v_item
+    _fields_ = [("kind", c_int), ("n_inputs", c_int), ("proof", c_void_p), ("proof_len", c_size_t),
+                ("vk", c_void_p), ("vk_len", c_size_t), ("inputs_be", c_void_p)]
 
 
 _lib = None
@@ -136,6 +146,22 @@ def load_library():
     lib.bn254v_launch_count.restype = c_uint64
     lib.bn254v_last_kernel_split.argtypes = [POINTER(c_float), POINTER(c_float)]
     lib.bn254v_last_kernel_split.restype = c_int
+    lib.bn254v_last_stage_ms.argtypes = [POINTER(c_float), c_int]
+    lib.bn254v_last_stage_ms.restype = c_int
+    lib.bn254v_plonk_batch_upload.argtypes = [c_void_p, u8p, c_size_t, u8p, c_int, u8p, c_size_t, POINTER(c_void_p)]
+    lib.bn254v_plonk_batch_upload.restype = c_int
+    lib.bn254v_plonk_batch_verify.argtypes = [c_void_p, c_void_p, u8p, POINTER(c_float)]
+    lib.bn254v_plonk_batch_verify.restype = c_int
+    lib.bn254v_pairing_batch_upload.argtypes = [u8p, u8p, c_int, c_size_t, POINTER(c_void_p)]
+    lib.bn254v_pairing_batch_upload.restype = c_int
+    lib.bn254v_pairing_batch_verify.argtypes = [c_void_p, u8p, POINTER(c_float)]
+    lib.bn254v_pairing_batch_verify.restype = c_int
+    lib.bn254v_vk_cache_get.argtypes = [c_int, u8p, c_size_t, c_int, POINTER(c_void_p)]
+    lib.bn254v_vk_cache_get.restype = c_int
+    lib.bn254v_vk_cache_size.restype = c_size_t
+    lib.bn254v_vk_cache_clear.restype = None
+    lib.bn254v_verify_many.argtypes = [POINTER(_Item), c_size_t, c_int, u8p, u8p]
+    lib.bn254v_verify_many.restype = c_int
     _lib = lib
     return lib
 
@@ -157,7 +183,7 @@ def init(devices=None):
 
 
 def shutdown():
-    _vk_cache.clear()
+    _vk_memo.clear()
     load_library().bn254v_shutdown()
 
 
@@ -201,40 +227,43 @@ def fr_to_be(values) -> np.ndarray:
 
 
 class _VkHandle:
+    """A handle owned by the library's VK cache (bn254v_vk_cache_get): never freed from here."""
+
     def __init__(self, ptr, kind):
         self.ptr, self.kind = ptr, kind
         self.n_public = load_library().bn254v_vk_n_public(ptr)
 
-    def __del__(self):
-        try:
-            if self.ptr and _lib is not None:
-                _lib.bn254v_vk_free(self.ptr)
-        except Exception:
-            pass
-
-
-_vk_cache: dict = {}
-
 
 def _vk(kind, vk_bytes, sign_mode=0) -> _VkHandle:
-    """VK handles are cached by sha256(vk) (SP1's *_vkey_hash): the VK-constant device tables are built once."""
+    """VK handles come from the library's cache, keyed by sha256(vk) (SP1's *_vkey_hash), kind and sign_mode: the
+    VK-constant device tables are built once (the reference re-parses the VK on every call)."""
     vk_bytes = bytes(vk_bytes)
-    key = (kind, sign_mode, hashlib.sha256(vk_bytes).digest())
-    h = _vk_cache.get(key)
-    if h is None:
-        lib = load_library()
-        out = c_void_p()
-        buf = np.frombuffer(vk_bytes, dtype=np.uint8)
-        if kind == "groth16":
-            rc = lib.bn254v_groth16_vk_load(_ptr(buf), len(vk_bytes), sign_mode, ctypes.byref(out))
-        else:
-            rc = lib.bn254v_plonk_vk_load(_ptr(buf), len(vk_bytes), ctypes.byref(out))
-        if rc == E_VK_PARSE:
-            raise VerifierPanic("VK_PARSE")  # the reference unwraps the VK parser (verifier/src/lib.rs:46,71)
-        _check(rc)
-        h = _VkHandle(out.value, kind)
-        _vk_cache[key] = h
+    memo_key = (kind, sign_mode, vk_bytes)
+    h = _vk_memo.get(memo_key)  # saves re-hashing a 34 KB PlonK VK on every call; the handles live in the C cache
+    if h is not None:
+        return h
+    lib = load_library()
+    out = c_void_p()
+    buf = np.frombuffer(vk_bytes, dtype=np.uint8)
+    rc = lib.bn254v_vk_cache_get(KIND_GROTH16 if kind == "groth16" else KIND_PLONK, _ptr(buf), len(vk_bytes), sign_mode,
+                                 ctypes.byref(out))
+    if rc == E_VK_PARSE:
+        raise VerifierPanic("VK_PARSE")  # the reference unwraps the VK parser (verifier/src/lib.rs:46,71)
+    _check(rc)
+    h = _vk_memo[memo_key] = _VkHandle(out.value, kind)
     return h
+
+
+_vk_memo: dict = {}
+
+
+def vk_cache_size() -> int:
+    return int(load_library().bn254v_vk_cache_size())
+
+
+def vk_cache_clear():
+    _vk_memo.clear()
+    load_library().bn254v_vk_cache_clear()
 
 
 def _pack_proofs(proofs):
@@ -298,15 +327,20 @@ class Groth16Verifier:
         raise VerifierPanic(status_name(st))
 
     @classmethod
-    def verify_batch(cls, proofs, vk, public_inputs, debug=False):
+    def verify_batch(cls, proofs, vk, public_inputs, debug=False, out=None):
         """Status byte per proof (numpy uint8).  `proofs`: list of gnark raw proofs (>= 256 bytes used) or an
-        (n, stride) uint8 array; `public_inputs`: per-proof Fr lists or an (n, k, 32) big-endian array."""
+        (n, stride) uint8 array; `public_inputs`: per-proof Fr lists or an (n, k, 32) big-endian array.
+        `out`: optional preallocated (n,) uint8 array (e.g. pinned memory) that receives the status bytes."""
         lib = load_library()
         h = _vk("groth16", vk, cls.sign_mode)
         arr, lens = _pack_proofs(proofs)
         n = arr.shape[0]
         inp, k = _pack_inputs(public_inputs, n)
-        status = np.full(n, STATUS_UNSET, dtype=np.uint8)
+        if out is None:
+            status = np.full(n, STATUS_UNSET, dtype=np.uint8)
+        else:
+            assert out.dtype == np.uint8 and out.shape == (n,) and out.flags["C_CONTIGUOUS"]
+            status = out
         dbg = DebugOutputs(n, 1, 0) if debug else None
         _check(lib.bn254v_groth16_verify_batch(h.ptr, _ptr(arr), arr.shape[1], _ptr(lens), _ptr(inp), k, n,
                                                _ptr(status), ctypes.byref(dbg.c) if dbg else None))
@@ -331,21 +365,26 @@ class PlonkVerifier:
         raise VerifierPanic(status_name(st))
 
     @classmethod
-    def verify_batch(cls, proofs, vk, public_inputs, rnd=None, debug=False):
-        """`rnd`: per-proof scalars replacing the reference's OsRng draw (verifier/src/plonk/kzg.rs:149-154);
-        None draws them from os.urandom."""
+    def verify_batch(cls, proofs, vk, public_inputs, rnd=None, debug=False, out=None):
+        """`rnd`: None (production) -- the library draws the batch-opening scalars from the OS CSPRNG where the reference
+        calls Fr::random(OsRng) (verifier/src/plonk/kzg.rs:149-154).  Explicit per-proof scalars are for tests and
+        reproducible runs only: a scalar the prover can predict makes the z-shifted opening forgeable (bn254v.h)."""
         lib = load_library()
         h = _vk("plonk", vk)
         arr, lens = _pack_proofs(proofs)
         n = arr.shape[0]
         inp, k = _pack_inputs(public_inputs, n)
         if rnd is None:
-            rnd_arr = np.frombuffer(os.urandom(32 * n), dtype=np.uint8).reshape(n, 32).copy()
+            rnd_arr = None
         elif isinstance(rnd, np.ndarray):
             rnd_arr = np.ascontiguousarray(rnd)
         else:
             rnd_arr = fr_to_be([int(v) % (1 << 256) for v in rnd])
-        status = np.full(n, STATUS_UNSET, dtype=np.uint8)
+        if out is None:
+            status = np.full(n, STATUS_UNSET, dtype=np.uint8)
+        else:
+            assert out.dtype == np.uint8 and out.shape == (n,) and out.flags["C_CONTIGUOUS"]
+            status = out
         dbg = DebugOutputs(n, 4, 8) if debug else None
         _check(lib.bn254v_plonk_verify_batch(h.ptr, _ptr(arr), arr.shape[1], _ptr(lens), _ptr(inp), k,
                                              _ptr(rnd_arr), n, _ptr(status), ctypes.byref(dbg.c) if dbg else None))
@@ -390,9 +429,29 @@ def pairing_synth(seed, n, k=4, first_index=0):
     return g1, g2, expected
 
 
-class Groth16DeviceBatch:
-    """A batch staged in HBM (bn254v_groth16_batch_upload) for kernel-only timing."""
+class _DeviceBatch:
+    """A batch staged in HBM (bn254v_*_batch_upload, include/bn254v_bench.h) for kernel-only timing."""
+    ptr = None
 
+    def _run(self, fn, args, want_status):
+        status = np.full(self.n, STATUS_UNSET, dtype=np.uint8) if want_status else None
+        ms = c_float(0)
+        _check(fn(*args, _ptr(status), ctypes.byref(ms)))
+        return status, ms.value
+
+    def free(self):
+        if self.ptr:
+            load_library().bn254v_batch_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Groth16DeviceBatch(_DeviceBatch):
     def __init__(self, vk_bytes, proofs, inputs, sign_mode=0):
         lib = load_library()
         self.vk = _vk("groth16", vk_bytes, sign_mode)
@@ -406,22 +465,45 @@ class Groth16DeviceBatch:
 
     def verify(self, want_status=True):
         """Returns (status or None, kernel milliseconds measured with CUDA events on the launching stream)."""
+        return self._run(load_library().bn254v_groth16_batch_verify, (self.vk.ptr, self.ptr), want_status)
+
+
+class PlonkDeviceBatch(_DeviceBatch):
+    def __init__(self, vk_bytes, proofs, inputs, rnd):
         lib = load_library()
-        status = np.full(self.n, STATUS_UNSET, dtype=np.uint8) if want_status else None
-        ms = c_float(0)
-        _check(lib.bn254v_groth16_batch_verify(self.vk.ptr, self.ptr, _ptr(status), ctypes.byref(ms)))
-        return status, ms.value
+        self.vk = _vk("plonk", vk_bytes)
+        proofs = np.ascontiguousarray(proofs, dtype=np.uint8)
+        inputs = np.ascontiguousarray(inputs, dtype=np.uint8)
+        rnd = np.ascontiguousarray(rnd, dtype=np.uint8)
+        self.n = proofs.shape[0]
+        out = c_void_p()
+        _check(lib.bn254v_plonk_batch_upload(self.vk.ptr, _ptr(proofs), proofs.shape[1], _ptr(inputs), inputs.shape[1],
+                                             _ptr(rnd), self.n, ctypes.byref(out)))
+        self.ptr = out.value
 
-    def free(self):
-        if self.ptr:
-            load_library().bn254v_batch_free(self.ptr)
-            self.ptr = None
+    def verify(self, want_status=True):
+        return self._run(load_library().bn254v_plonk_batch_verify, (self.vk.ptr, self.ptr), want_status)
 
-    def __del__(self):
-        try:
-            self.free()
-        except Exception:
-            pass
+
+class PairingDeviceBatch(_DeviceBatch):
+    def __init__(self, g1, g2, k):
+        lib = load_library()
+        g1 = np.ascontiguousarray(g1, dtype=np.uint8)
+        g2 = np.ascontiguousarray(g2, dtype=np.uint8)
+        self.n = g1.size // (64 * k)
+        out = c_void_p()
+        _check(lib.bn254v_pairing_batch_upload(_ptr(g1), _ptr(g2), k, self.n, ctypes.byref(out)))
+        self.ptr = out.value
+
+    def verify(self, want_status=True):
+        return self._run(load_library().bn254v_pairing_batch_verify, (self.ptr,), want_status)
+
+
+def last_stage_ms():
+    """Device times of the stages of the last *DeviceBatch.verify() (bn254v_last_stage_ms)."""
+    buf = (c_float * 8)()
+    n = load_library().bn254v_last_stage_ms(buf, 8)
+    return [buf[i] for i in range(n)]
 
 
 def last_kernel_split():
@@ -439,25 +521,30 @@ def imad_peak(iters=4096):
     return {"wide_mac_per_s": wide.value, "lo_mac_per_s": lo.value, "sm_clock_mhz": clk.value}
 
 
-def verify_many(items, rnd=None):
-    """Mixed batch over several verifying keys and both proof systems: `items` is a list of
-    (kind, proof_bytes, vk_bytes, public_inputs) with kind in {"groth16", "plonk"}.  Items are grouped by
-    (kind, sha256(vk)) -- one device batch per group, VK handles cached -- and the status bytes come back in input order.
-    `rnd`: optional per-item scalars for the PlonK items (kzg.rs:149-154); None draws them from os.urandom."""
-    groups = {}
-    for pos, (kind, proof, vk, inputs) in enumerate(items):
+def verify_many(items, rnd=None, sign_mode=0):
+    """Mixed batch over several verifying keys and both proof systems (bn254v_verify_many): `items` is a list of
+    (kind, proof_bytes, vk_bytes, public_inputs) with kind in {"groth16", "plonk"}.  The library groups the items by
+    (kind, sha256(vk), number of inputs) -- one device batch per group, VK handles cached inside the library -- and
+    the status bytes come back in input order.  `rnd`: None (production: drawn inside the library), or per-item scalars
+    for the PlonK items (tests only, see bn254v.h)."""
+    lib = load_library()
+    n = len(items)
+    arr = (_Item * max(n, 1))()
+    keep = []  # buffers referenced by the item array
+    vk_bufs = {}
+    for i, (kind, proof, vk, inputs) in enumerate(items):
         if kind not in ("groth16", "plonk"):
             raise ValueError("kind must be 'groth16' or 'plonk'")
         vk = bytes(vk)
-        groups.setdefault((kind, hashlib.sha256(vk).digest(), len(inputs)), [vk, []])[1].append(pos)
-    out = np.full(len(items), STATUS_UNSET, dtype=np.uint8)
-    for (kind, _, _), (vk, positions) in groups.items():
-        proofs = [items[p][1] for p in positions]
-        inputs = [list(items[p][3]) for p in positions]
-        if kind == "groth16":
-            st = Groth16Verifier.verify_batch(proofs, vk, inputs)
-        else:
-            r = None if rnd is None else [rnd[p] for p in positions]
-            st = PlonkVerifier.verify_batch(proofs, vk, inputs, rnd=r)
-        out[np.asarray(positions)] = st
+        vb = vk_bufs.get(vk)
+        if vb is None:
+            vb = vk_bufs[vk] = np.frombuffer(vk, dtype=np.uint8)
+        pb = np.frombuffer(bytes(proof), dtype=np.uint8) if len(proof) else np.zeros(1, np.uint8)
+        ib = fr_to_be(list(inputs)) if len(inputs) else np.zeros((1, 32), np.uint8)
+        keep += [pb, ib]
+        arr[i] = _Item(KIND_GROTH16 if kind == "groth16" else KIND_PLONK, len(inputs), pb.ctypes.data, len(proof),
+                       vb.ctypes.data, len(vk), ib.ctypes.data)
+    rnd_arr = None if rnd is None else fr_to_be([int(v) % (1 << 256) for v in rnd])
+    out = np.full(n, STATUS_UNSET, dtype=np.uint8)
+    _check(lib.bn254v_verify_many(arr, n, sign_mode, _ptr(rnd_arr), _ptr(out)))
     return out

@@ -9,4 +9,21 @@ namespace bn254 {
 
 #include "curve_body.inc"
 
+// group generators (substitute inputs for masked / failed proofs, synthetic workloads)
+HD G1Aff g1_generator() {
+  G1Aff g;
+  BN_LOAD_FP(g.x, K::g1_gen, 0);
+  BN_LOAD_FP(g.y, K::g1_gen, 1);
+  return g;
+}
+HD G2Aff g2_generator_dev() {
+  G2Aff g;
+  BN_LOAD_FP(g.x.c0, K::g2_gen, 0);
+  BN_LOAD_FP(g.x.c1, K::g2_gen, 1);
+  BN_LOAD_FP(g.y.c0, K::g2_gen, 2);
+  BN_LOAD_FP(g.y.c1, K::g2_gen, 3);
+  return g;
+}
+
+
 }  // namespace bn254

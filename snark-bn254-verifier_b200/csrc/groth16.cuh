@@ -95,58 +95,86 @@ struct Groth16Debug {
 // The verification in two halves, so that the batch kernels can run them as two launches (each with half the code
 // and half the stack): (1) decode, validate, prepare_inputs, Miller loop -> the Fq12 Miller value;
 // (2) final exponentiation and comparison with e(alpha, beta').
+// Barrier discipline: miller_loop_pairtab / final_exponentiation contain block-wide phase barriers, so every thread of a
+// block must reach them the same number of times.  A proof that fails before the Miller loop is therefore NOT ended
+// early: its status is recorded and the thread runs the loop on substitute VK points (always valid, order r), whose
+// result is discarded.  `live == false` (a spare thread of the last block) does the same and writes nothing.
 HD int groth16_miller_one(Fp12& f, const Groth16VkDev& vk, const uint8_t* proof, uint32_t proof_len,
-                          const uint8_t* inputs_be, int n_inputs, const Groth16Debug& dbg) {
-  if (proof_len < 256) return BN254V_PANIC_SHORT_BUFFER;
-  G1Aff A, C;
+                          const uint8_t* inputs_be, int n_inputs, const Groth16Debug& dbg, bool live = true) {
+  G1Aff A, C, L;
   G2Aff B;
-  int st = load_g1_checked(A, proof);
-  if (st != BN254V_OK_TRUE) return st;
-  st = load_g2_on_curve(B, proof + 64);
-  if (st != BN254V_OK_TRUE) return st;
-  // B's subgroup test (the last check of AffineG2::new) is read off the end point of the Miller loop below.  The
-  // reference parses B before C and before the public inputs, so on a later failure B's verdict still comes first
-  // (rare path, separate scalar multiplication, no barriers).
-  G1Aff L;
-  st = load_g1_checked(C, proof + 192);
-  if (st == BN254V_OK_TRUE) st = groth16_prepare_inputs(L, vk, inputs_be, n_inputs);
-  if (st != BN254V_OK_TRUE) return g2_in_subgroup<false>(B) ? st : BN254V_PANIC_NOT_IN_SUBGROUP;
+  int st = BN254V_OK_TRUE;
+  if (!live) st = BN254V_STATUS_UNSET;
+  else if (proof_len < 256) st = BN254V_PANIC_SHORT_BUFFER;
+  if (st == BN254V_OK_TRUE) st = load_g1_checked(A, proof);
+  if (st == BN254V_OK_TRUE) {
+    st = load_g2_on_curve(B, proof + 64);
+    if (st == BN254V_OK_TRUE) {
+      // B's subgroup test (the last check of AffineG2::new) is read off the end point of the Miller loop below.  The
+      // reference parses B before C and before the public inputs, so on a later failure B's verdict still comes first
+      // (rare path, separate scalar multiplication, no barriers).
+      st = load_g1_checked(C, proof + 192);
+      if (st == BN254V_OK_TRUE) st = groth16_prepare_inputs(L, vk, inputs_be, n_inputs);
+      if (st != BN254V_OK_TRUE && !g2_in_subgroup<false>(B)) st = BN254V_PANIC_NOT_IN_SUBGROUP;
+    }
+  }
+  const bool ok = st == BN254V_OK_TRUE;
+  if (!ok) A = vk.alpha, B = vk.beta, L = vk.ic[0], C = vk.ic[0];  // substitute inputs; the result is discarded
 
   G1Aff pf[2] = {L, C};
   bool in_g2;
   miller_loop_pairtab<1>(f, &A, &B, pf, vk.gd_pairs, &in_g2);
+  if (!ok) return st;
   if (!in_g2) return BN254V_PANIC_NOT_IN_SUBGROUP;
   if (dbg.L) store_g1(dbg.L, L);
   if (dbg.miller) fp12_to_bytes(dbg.miller, f);
   return BN254V_OK_TRUE;
 }
-HD int groth16_finish_one(Fp12& f, const Groth16VkDev& vk, const Groth16Debug& dbg) {
+// `decide == false`: run the exponentiation for its barriers only (the proof already has its status).
+HD int groth16_finish_one(Fp12& f, const Groth16VkDev& vk, const Groth16Debug& dbg, bool decide = true) {
   final_exponentiation(f, f);
+  if (!decide) return BN254V_STATUS_UNSET;
   if (dbg.gt) fp12_to_bytes(dbg.gt, f);
   return eq(f, vk.target) ? BN254V_OK_TRUE : BN254V_OK_FALSE;
 }
 
-// proof: >= 256 bytes (A | B | C), proof_len: valid bytes.
+// proof: >= 256 bytes (A | B | C), proof_len: valid bytes.  Returns BN254V_STATUS_UNSET for a spare thread.
 HD int groth16_verify_one(const Groth16VkDev& vk, const uint8_t* proof, uint32_t proof_len,
-                          const uint8_t* inputs_be, int n_inputs, const Groth16Debug& dbg) {
+                          const uint8_t* inputs_be, int n_inputs, const Groth16Debug& dbg, bool live = true) {
   Fp12 f;
-  int st = groth16_miller_one(f, vk, proof, proof_len, inputs_be, n_inputs, dbg);
-  if (st != BN254V_OK_TRUE) return st;
-  return groth16_finish_one(f, vk, dbg);
+  int st = groth16_miller_one(f, vk, proof, proof_len, inputs_be, n_inputs, dbg, live);
+  const bool ok = st == BN254V_OK_TRUE;
+  if (!ok) f = vk.target;  // any non-zero value: the exponentiation runs for its barriers only
+  int st2 = groth16_finish_one(f, vk, dbg, ok);
+  return ok ? st2 : st;
 }
 
-// Raw k-pair product (bn::pairing_batch): all G2 variable.  A pair whose G1 bytes are all zero is
-// skipped (identity).  Returns is_one.
+// Raw k-pair product (bn::pairing_batch): all G2 variable.  A pair with an identity member -- encoded as all-zero
+// bytes: 64 for G1, 128 for G2 -- is skipped, as substrate-bn's pairing_batch skips it: the thread still walks the
+// loop on generator points (barriers, uniform control flow) with that pair masked out, i.e. its lines replaced by the
+// sparse element 1, so the Miller value is exactly the product over the remaining pairs.  Returns is_one.
+HD bool all_zero_bytes(const uint8_t* b, int n) {
+  uint32_t t = 0;
+  for (int i = 0; i < n; i++) t |= b[i];
+  return t == 0;
+}
 template <int KP>
 HD bool pairing_product_one(const uint8_t* g1, const uint8_t* g2, uint8_t* miller_out, uint8_t* gt_out) {
   G1Aff p[KP];
   G2Aff q[KP];
+  uint32_t skip = 0;
   for (int j = 0; j < KP; j++) {
-    load_g1_unchecked(p[j], g1 + 64 * j);
-    load_g2_unchecked(q[j], g2 + 128 * j);
+    if (all_zero_bytes(g1 + 64 * j, 64) || all_zero_bytes(g2 + 128 * j, 128)) {
+      skip |= 1u << j;
+      p[j] = g1_generator();
+      q[j] = g2_generator_dev();
+    } else {
+      load_g1_unchecked(p[j], g1 + 64 * j);
+      load_g2_unchecked(q[j], g2 + 128 * j);
+    }
   }
   Fp12 f;
-  miller_loop<KP, 0>(f, p, q, nullptr, nullptr);
+  miller_loop<KP, 0>(f, p, q, nullptr, nullptr, skip);
   if (miller_out) fp12_to_bytes(miller_out, f);
   final_exponentiation(f, f);
   if (gt_out) fp12_to_bytes(gt_out, f);

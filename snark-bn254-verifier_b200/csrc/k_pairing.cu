@@ -1,0 +1,50 @@
+// Raw k-pair pairing-product kernels (bn::pairing_batch; reference call sites verifier/src/groth16/verify.rs:70-77,
+// verifier/src/plonk/kzg.rs:180-187), one set per thread.  sm_100a only.
+#include "kernels.h"
+
+namespace bn254 {
+namespace {
+
+template <int KP, int TPB>
+__global__ void __launch_bounds__(TPB, 1)
+    k_pairing_product(const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2, size_t n,
+                      uint8_t* __restrict__ is_one, uint8_t* miller_out, uint8_t* gt_out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n;
+  if (!live) i = n - 1;  // spare threads walk the last set (phase barriers inside) and write nothing
+  bool one = pairing_product_one<KP>(g1 + (size_t)64 * KP * i, g2 + (size_t)128 * KP * i,
+                                     live && miller_out ? miller_out + 384 * i : nullptr,
+                                     live && gt_out ? gt_out + 384 * i : nullptr);
+  if (live) is_one[i] = one ? 1 : 0;
+}
+
+template <int KP>
+void launch_k(cudaStream_t st, const uint8_t* g1, const uint8_t* g2, size_t m, uint8_t* is_one, uint8_t* ml, uint8_t* gt,
+              int shape) {
+#define PP(TPB) k_pairing_product<KP, TPB><<<(unsigned)((m + TPB - 1) / TPB), TPB, 0, st>>>(g1, g2, m, is_one, ml, gt)
+  switch (shape) {
+    case launch::SHAPE_448: case launch::SHAPE_384: PP(448); break;
+    case launch::SHAPE_32: PP(32); break;
+    default: PP(128); break;
+  }
+#undef PP
+}
+
+}  // namespace
+
+namespace launch {
+
+int pairing_product(cudaStream_t st, int k, const uint8_t* g1, const uint8_t* g2, size_t m, uint8_t* is_one,
+                    uint8_t* miller_out, uint8_t* gt_out, int sm_count) {
+  const int shape = pick_shape(m, sm_count);
+  switch (k) {
+    case 1: launch_k<1>(st, g1, g2, m, is_one, miller_out, gt_out, shape); break;
+    case 2: launch_k<2>(st, g1, g2, m, is_one, miller_out, gt_out, shape); break;
+    case 3: launch_k<3>(st, g1, g2, m, is_one, miller_out, gt_out, shape); break;
+    default: launch_k<4>(st, g1, g2, m, is_one, miller_out, gt_out, shape); break;
+  }
+  return 1;
+}
+
+}  // namespace launch
+}  // namespace bn254

@@ -1,0 +1,124 @@
+// PlonK batch kernels, staged (plonk.cuh): A (per proof) -> terms 0 (per proof x term) -> C (per survivor) -> terms 1
+// -> E (per survivor: sums, 2-pair Miller loop, final exponentiation).  sm_100a only.
+// Replaces, per proof, load_plonk_proof_from_bytes + verify_plonk (reference verifier/src/plonk/converter.rs:121-178,
+// verifier/src/plonk/verify.rs:46-317, verifier/src/plonk/kzg.rs:46-190).
+// `list` holds the indices of the proofs that are still alive after stage A (early rejects cost nothing further);
+// a slot is set to -(i + 1) when stage C ends the proof.
+#include "kernels.h"
+
+namespace bn254 {
+namespace {
+
+struct PlonkDbgPtrs {
+  uint8_t *g1, *fr, *m, *gt;
+};
+__device__ __forceinline__ PlonkDebug plonk_dbg(const PlonkDbgPtrs& d, size_t i) {
+  return PlonkDebug{d.g1 ? d.g1 + 256 * i : nullptr, d.fr ? d.fr + 256 * i : nullptr, d.m ? d.m + 384 * i : nullptr,
+                    d.gt ? d.gt + 384 * i : nullptr};
+}
+
+__global__ void k_plonk_vk_prepare(PlonkVkDev* vk) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) plonk_vk_prepare(*vk);
+}
+__global__ void k_plonk_fixed_tables(const G1Aff* bases, G1Aff* table) {
+  int b = blockIdx.x, w = threadIdx.x;
+  if (w >= BN_IC_WINDOWS) return;
+  groth16_ic_table_slice(table + ((size_t)b * BN_IC_WINDOWS + w) * BN_IC_ENTRIES, bases[b], w);
+}
+
+__global__ void __launch_bounds__(64)
+    k_plonk_stage_a(const PlonkVkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride,
+                    const uint32_t* __restrict__ proof_len, const uint8_t* __restrict__ inputs, int n_inputs, size_t n,
+                    uint8_t* __restrict__ status, PlonkWork* work, int* list, int* count, PlonkDbgPtrs dp) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;  // (no barriers in stages A, C and the term kernels)
+  uint32_t len = proof_len ? proof_len[i] : (uint32_t)stride;
+  if (len > stride) len = (uint32_t)stride;
+  int st = plonk_stage_a(work[i], *vk, proofs + stride * i, len, inputs + (size_t)32 * n_inputs * i, n_inputs,
+                         plonk_dbg(dp, i));
+  if (st == BN254V_OK_TRUE) {
+    list[atomicAdd(count, 1)] = (int)i;
+    status[i] = BN254V_STATUS_UNSET;
+  } else {
+    status[i] = (uint8_t)st;
+  }
+}
+
+__global__ void __launch_bounds__(64)
+    k_plonk_terms(const PlonkVkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride, PlonkWork* work,
+                  const int* __restrict__ list, const int* __restrict__ count, int stage) {
+  int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= *count) return;
+  int i = list[slot];
+  if (i < 0) return;
+  plonk_term(work[i], *vk, proofs + stride * (size_t)i, stage, blockIdx.y);
+}
+
+__global__ void __launch_bounds__(64)
+    k_plonk_stage_c(const PlonkVkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride,
+                    const uint8_t* __restrict__ rnd, uint8_t* __restrict__ status, PlonkWork* work, int* list,
+                    const int* __restrict__ count, PlonkDbgPtrs dp) {
+  int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= *count) return;
+  int i = list[slot];
+  int st = plonk_stage_c(work[i], *vk, proofs + stride * (size_t)i, rnd + (size_t)32 * i, plonk_dbg(dp, i));
+  if (st != BN254V_OK_TRUE) {
+    status[i] = (uint8_t)st;
+    list[slot] = -(i + 1);  // dead: the term kernel skips it, stage E walks the pairing on substitute points
+  }
+}
+
+// Stage E contains the pairing's block-wide phase barriers: every thread of every launched block runs it to the end
+// (a block with no survivor at all leaves as a whole -- a block-uniform exit).
+template <int TPB>
+__global__ void __launch_bounds__(TPB, 1)
+    k_plonk_stage_e(const PlonkVkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride,
+                    uint8_t* __restrict__ status, PlonkWork* work, const int* __restrict__ list,
+                    const int* __restrict__ count, PlonkDbgPtrs dp) {
+  const int cnt = *count;
+  if ((int)(blockIdx.x * blockDim.x) >= cnt) return;  // uniform over the block
+  int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  bool live = slot < cnt;
+  int i = list[live ? slot : cnt - 1];
+  if (i < 0) live = false, i = -(i + 1);
+  PlonkDebug dbg = live ? plonk_dbg(dp, i) : PlonkDebug{nullptr, nullptr, nullptr, nullptr};
+  int st = plonk_stage_e(work[i], *vk, proofs + stride * (size_t)i, dbg, live);
+  if (live) status[i] = (uint8_t)st;
+}
+
+}  // namespace
+
+namespace launch {
+
+int plonk_vk_prepare(cudaStream_t st, PlonkVkDev* dv, int n_fixed, G1Aff* bases_then_tables) {
+  k_plonk_vk_prepare<<<1, 32, 0, st>>>(dv);
+  k_plonk_fixed_tables<<<n_fixed, BN_IC_WINDOWS, 0, st>>>(bases_then_tables, bases_then_tables + n_fixed);
+  return 2;
+}
+
+int plonk_verify(cudaStream_t st, const PlonkArgs& a, int sm_count) {
+  const size_t cm = a.m;
+  PlonkDbgPtrs dp{a.dbg_g1, a.dbg_fr, a.dbg_m, a.dbg_gt};
+  const unsigned g64 = (unsigned)((cm + 63) / 64);
+  const int n_terms = a.n_qcp + 10;
+  cudaMemsetAsync(a.count, 0, sizeof(int), st);
+  k_plonk_stage_a<<<g64, 64, 0, st>>>(a.vk, a.proofs, a.stride, a.lens, a.inputs, a.n_inputs, cm, a.status, a.work,
+                                      a.list, a.count, dp);
+  if (a.stage_ev) cudaEventRecord(a.stage_ev[0], st);
+  k_plonk_terms<<<dim3(g64, n_terms), 64, 0, st>>>(a.vk, a.proofs, a.stride, a.work, a.list, a.count, 0);
+  if (a.stage_ev) cudaEventRecord(a.stage_ev[1], st);
+  k_plonk_stage_c<<<g64, 64, 0, st>>>(a.vk, a.proofs, a.stride, a.rnd, a.status, a.work, a.list, a.count, dp);
+  if (a.stage_ev) cudaEventRecord(a.stage_ev[2], st);
+  k_plonk_terms<<<dim3(g64, n_terms), 64, 0, st>>>(a.vk, a.proofs, a.stride, a.work, a.list, a.count, 1);
+  if (a.stage_ev) cudaEventRecord(a.stage_ev[3], st);
+  if (pick_shape(cm, sm_count) == SHAPE_32)
+    k_plonk_stage_e<32><<<(unsigned)((cm + 31) / 32), 32, 0, st>>>(a.vk, a.proofs, a.stride, a.status, a.work, a.list,
+                                                                   a.count, dp);
+  else
+    k_plonk_stage_e<128><<<(unsigned)((cm + 127) / 128), 128, 0, st>>>(a.vk, a.proofs, a.stride, a.status, a.work,
+                                                                       a.list, a.count, dp);
+  return 5;
+}
+
+}  // namespace launch
+}  // namespace bn254

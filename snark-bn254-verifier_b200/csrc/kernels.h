@@ -1,0 +1,70 @@
+// Launch interface between the host side of the library (bn254v.cu: C ABI, sharding, buffers) and the kernel
+// translation units (k_groth16.cu, k_plonk.cu, k_pairing.cu, k_aux.cu).  Each kernel TU is compiled on its own (the
+// pairing code is large; four nvcc processes in parallel build the library in a third of the time) and exposes plain
+// host functions that enqueue its kernels on a stream and return how many launches they issued.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "plonk.cuh"
+#include "synth.cuh"
+
+namespace bn254 {
+namespace launch {
+
+// Launch shape of the per-proof pairing kernels for a batch of m items (see k_groth16.cu).
+enum Shape { SHAPE_32 = 6, SHAPE_128 = 1, SHAPE_448 = 3, SHAPE_384 = 10 };
+int pick_shape(size_t m, int sm_count);
+
+// ---- VK-constant precomputation (once per VK and device)
+int groth16_vk_prepare(cudaStream_t st, Groth16VkDev* dv, int n_bases, G1Aff* table);
+int plonk_vk_prepare(cudaStream_t st, PlonkVkDev* dv, int n_fixed, G1Aff* bases_then_tables);
+
+// ---- Groth16 batch on device-resident buffers
+struct Groth16Args {
+  const Groth16VkDev* vk;
+  const uint8_t* proofs;
+  size_t stride;
+  const uint32_t* lens;  // or null
+  const uint8_t* inputs;
+  int n_inputs;
+  size_t m;
+  uint8_t* status;
+  uint8_t *dbg_l, *dbg_m, *dbg_gt;  // or null
+  Fp12* fbuf;                       // m Miller values (two-launch shapes), or null
+  cudaEvent_t mid;                  // recorded between the two launches when non-null
+};
+int groth16_verify(cudaStream_t st, const Groth16Args& a, int sm_count, bool* two_launch);
+
+// ---- PlonK chunk (<= 2^16 proofs) on device-resident buffers
+struct PlonkArgs {
+  const PlonkVkDev* vk;
+  int n_qcp;
+  const uint8_t* proofs;
+  size_t stride;
+  const uint32_t* lens;  // or null
+  const uint8_t* inputs;
+  int n_inputs;
+  const uint8_t* rnd;
+  size_t m;
+  uint8_t* status;
+  uint8_t *dbg_g1, *dbg_fr, *dbg_m, *dbg_gt;  // or null
+  PlonkWork* work;                            // m records
+  int* list;                                  // m slots
+  int* count;                                 // 1 counter
+  cudaEvent_t* stage_ev;                      // 4 events recorded after stages A, terms 0, C, terms 1, or null
+};
+int plonk_verify(cudaStream_t st, const PlonkArgs& a, int sm_count);
+
+// ---- raw pairing products
+int pairing_product(cudaStream_t st, int k, const uint8_t* g1, const uint8_t* g2, size_t m, uint8_t* is_one,
+                    uint8_t* miller_out, uint8_t* gt_out, int sm_count);
+
+// ---- synthetic workloads and the roofline probe (k_aux.cu)
+int groth16_synth(cudaStream_t st, const Groth16Trapdoor& td, uint64_t seed, size_t first, size_t n, int n_public,
+                  int sign_mode, uint8_t* proofs, uint8_t* inputs, uint8_t* expected);
+int pairing_synth(cudaStream_t st, uint64_t seed, size_t first, size_t n, int k, uint8_t* g1, uint8_t* g2,
+                  uint8_t* expected);
+int imad_peak(cudaStream_t st, bool wide, int blocks, int threads, int iters, uint64_t* sink);
+
+}  // namespace launch
+}  // namespace bn254

@@ -73,21 +73,6 @@ HD void synth_base_scalars(Fr* xs, Fr& a, Fr& b, Fr& c, const Groth16Trapdoor& t
   c = fe_mul(num, td.delta_inv);
 }
 
-HD G1Aff g1_generator() {
-  G1Aff g;
-  BN_LOAD_FP(g.x, K::g1_gen, 0);
-  BN_LOAD_FP(g.y, K::g1_gen, 1);
-  return g;
-}
-HD G2Aff g2_generator_dev() {
-  G2Aff g;
-  BN_LOAD_FP(g.x.c0, K::g2_gen, 0);
-  BN_LOAD_FP(g.x.c1, K::g2_gen, 1);
-  BN_LOAD_FP(g.y.c0, K::g2_gen, 2);
-  BN_LOAD_FP(g.y.c1, K::g2_gen, 3);
-  return g;
-}
-
 HD void store_g1_mul_gen(uint8_t* out, const Fr& k_mont) {
   Fr k = fe_from_mont(k_mont);
   G1Aff p;

@@ -9,19 +9,49 @@ import pytest
 from conftest import ROOT
 
 
-def _header_functions():
-    src = open(os.path.join(ROOT, "include", "bn254v.h")).read()
+def _header_functions(name):
+    src = open(os.path.join(ROOT, "include", name)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(bn254v_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_library_exports_every_declared_symbol(pkg):
     lib = pkg.load_library()
-    declared = _header_functions()
-    assert len(declared) >= 19
-    for name in declared:
+    declared = _header_functions("bn254v.h")
+    assert len(declared) >= 16
+    bench = _header_functions("bn254v_bench.h")
+    assert len(bench) >= 13
+    for name in declared + bench:
         assert hasattr(lib, name), name
     assert sorted(pkg.EXPORTS) == declared
+    assert sorted(pkg.BENCH_EXPORTS) == bench
+    # measurement / synthetic-workload helpers are not part of the verifier's header
+    assert not any(n in declared for n in ("bn254v_imad_peak", "bn254v_groth16_synth", "bn254v_launch_count"))
+
+
+def test_stale_check_tracks_inc_files(pkg):
+    """An edit to a .inc body (most of the arithmetic) must trigger a rebuild."""
+    b = pkg._build
+    deps = [os.path.basename(p) for p in b._deps()]
+    assert "tower_body.inc" in deps and "pairing_body.inc" in deps and "bn254v_bench.h" in deps
+    assert not b.is_stale()
+    p = os.path.join(b.CSRC, "tower_body.inc")
+    st = os.stat(p)
+    try:
+        os.utime(p, (st.st_atime, os.path.getmtime(b.LIB) + 10))
+        assert b.is_stale()
+    finally:
+        os.utime(p, (st.st_atime, st.st_mtime))
+    assert not b.is_stale()
+    old = os.environ.get("BN254V_NVCC_EXTRA")
+    try:
+        os.environ["BN254V_NVCC_EXTRA"] = "-DBN_SYNC_FINE"
+        assert b.is_stale()  # other flags than the library was built with
+    finally:
+        if old is None:
+            del os.environ["BN254V_NVCC_EXTRA"]
+        else:
+            os.environ["BN254V_NVCC_EXTRA"] = old
 
 
 def test_status_names(pkg):
