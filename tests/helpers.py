@@ -129,3 +129,73 @@ def plonk_structural_suite(prog="fibonacci"):
     out.append(("zu == r", bytes(b), xs))
     out.append(("trailing bytes", raw + bytes(40), xs))
     return out
+
+
+def plonk_shape_variant(nqcp, nb_public, prog="fibonacci"):
+    """A PlonK (vk bytes, proof bytes, inputs) of another circuit shape than the one bundled VK (nQcp = 1, nPub = 2),
+    derived from the bundled fixture: `nqcp` BSB22 commitments / Qcp points / commitment indexes and `nb_public` public
+    inputs.  No prover exists for these shapes, so claimed[0] is SOLVED to equal the constant term of the linearised
+    polynomial (it enters no earlier challenge): the proof then passes the OpeningPolyMismatch check, runs both MSM
+    rounds and the pairing, and fails there -- every intermediate (challenges, PI, digests, pairing inputs, Fq12
+    values) is defined and can be compared with the oracle."""
+    import plonk_oracle as po
+    raw, xs = plonk_fixture(prog)
+    vk = plonk_vk_bytes()
+    head, nq0 = vk[:368], int.from_bytes(vk[368:372], "big")
+    assert nq0 == 1
+    qcp0 = vk[372:404]
+    rest = vk[404:404 + 160 + 33788]           # g1, g2[0], g2[1], zero-filled lines
+    tail = vk[404 + 160 + 33788:]
+    assert int.from_bytes(tail[:8], "big") == 1
+    cci0 = int.from_bytes(tail[8:16], "big")
+    extra_qcp = [vk[112 + 32 * 3:112 + 32 * 4], vk[112 + 32 * 4:112 + 32 * 5], vk[112 + 32 * 5:112 + 32 * 6]]  # Ql Qr Qm
+    qcps = ([qcp0] + extra_qcp)[:nqcp]
+    ccis = [cci0 + 3 * i for i in range(nqcp)]
+    head = head[:72] + nb_public.to_bytes(8, "big") + head[80:]
+    new_vk = head + nqcp.to_bytes(4, "big") + b"".join(qcps) + rest + len(ccis).to_bytes(8, "big") + \
+        b"".join(c.to_bytes(8, "big") for c in ccis)
+    # proof: 8 points | ncl | claimed | zsH zu | nbsb | bsb..
+    pts = raw[:512]
+    claimed = [raw[516 + 32 * i:548 + 32 * i] for i in range(7)]
+    off = 516 + 32 * 7
+    zsh_zu = raw[off:off + 96]
+    bsb0 = raw[off + 100:off + 164]
+    bsbs = ([bsb0] + [raw[64 * i:64 * i + 64] for i in range(3)])[:nqcp]      # further commitments: L R O (valid points)
+    cl = claimed[:6] + [claimed[6]] * nqcp
+    inputs = (list(xs) + [12345, 67890, 13579])[:nb_public]
+
+    def build(c0):
+        c = [c0] + cl[1:]
+        return pts + len(c).to_bytes(4, "big") + b"".join(c) + zsh_zu + len(bsbs).to_bytes(4, "big") + b"".join(bsbs)
+
+    d = {}
+    try:
+        po.plonk_verifier_verify(build(cl[0]), new_vk, inputs, rnd=99, debug=d)
+    except po.PlonkError as e:
+        assert e.kind == "OPENING_POLY_MISMATCH", e.kind
+    proof = build(d["const_lin"].to_bytes(32, "big"))
+    return new_vk, proof, inputs
+
+
+TWIST_COFACTOR_SMALL_PRIMES = (10069, 5864401, 1875725156269)
+
+
+def random_twist_point(rng):
+    """A random point of E'(Fq2) (almost surely outside G2: the cofactor is ~2^254)."""
+    while True:
+        x = (int(rng.integers(0, 1 << 62)) * int(rng.integers(1, 1 << 62)) % bo.P, int(rng.integers(0, 1 << 62)) % bo.P)
+        y = bo.fp2_sqrt(bo.fp2_add(bo.fp2_mul(bo.fp2_sqr(x), x), bo.B2))
+        if y is not None:
+            if int(rng.integers(0, 2)):
+                y = bo.fp2_neg(y)
+            return (x, y)
+
+
+def twist_point_of_order(ell, rng):
+    """A point of E'(Fq2) of exact prime order ell (ell divides the cofactor 2p - r)."""
+    n_twist = bo.R * (2 * bo.P - bo.R)
+    while True:
+        pt = bo.g2_mul_raw(random_twist_point(rng), n_twist // ell)
+        if pt is not None:
+            assert bo.g2_mul_raw(pt, ell) is None
+            return pt

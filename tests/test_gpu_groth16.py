@@ -151,3 +151,95 @@ def test_full_size_sample_against_cpp_oracle(gpu):
                                                             debug=True)
     assert (status == st_c).all() and (status == expected[idx]).all()
     assert (dbg.g1[:, 0] == l_c).all() and (dbg.miller == ml_c).all() and (dbg.gt == gt_c).all()
+
+
+def test_g2_membership_hardening(gpu):
+    """The end-point subgroup test (csrc/pairing_body.inc, ate_endpoint_in_g2) on the device against the reference's
+    predicate [r]Q == O (verifier/src/converter.rs:135-153 -> AffineG2::new): >= 4096 points of E'(Fq2) as the proof's
+    B -- random points outside G2, points of each small prime order dividing the cofactor, products of those, sums of
+    an order-r point with a small-order point -- next to points of G2.  Every status equals the C++ oracle's and, on a
+    sample and on all small-order classes, the Python oracle's."""
+    import os
+    import ref_cpu
+    from helpers import TWIST_COFACTOR_SMALL_PRIMES, random_twist_point, twist_point_of_order
+    rng = np.random.default_rng(20260118)
+    td = bo.Groth16Trapdoor(31, 2, 0)
+    vk = td.vk_bytes()
+    pb, xs, _ = td.proof(0, corrupt=False)
+    points, klass = [], []
+    for _ in range(3800):
+        points.append(random_twist_point(rng)), klass.append("random")
+    small = {ell: [twist_point_of_order(ell, rng) for _ in range(24)] for ell in TWIST_COFACTOR_SMALL_PRIMES}
+    for ell, pts in small.items():
+        for p in pts:
+            points.append(p), klass.append("order %d" % ell)
+    l0, l1, l2 = TWIST_COFACTOR_SMALL_PRIMES
+    for i in range(24):  # composite small order
+        points.append(bo.g2_add(small[l0][i], small[l1][i])), klass.append("order l0*l1")
+        points.append(bo.g2_add(small[l1][i], small[l2][i])), klass.append("order l1*l2")
+    in_g2 = [bo.g2_mul(bo.G2_GEN, int(rng.integers(1, 1 << 62))) for _ in range(96)]
+    for i in range(72):  # an order-r point plus a small-order point
+        ell = TWIST_COFACTOR_SMALL_PRIMES[i % 3]
+        points.append(bo.g2_add(in_g2[i], small[ell][i % 24])), klass.append("G2 + order %d" % ell)
+    for p in in_g2:
+        points.append(p), klass.append("in G2")
+    n = len(points)
+    assert n >= 4096
+    proofs = np.tile(np.frombuffer(pb, np.uint8), (n, 1)).copy()
+    for i, p in enumerate(points):
+        proofs[i, 64:192] = np.frombuffer(bo.g2_to_bytes(p), np.uint8)
+    inputs = np.tile(gpu.fr_to_be(xs)[None], (n, 1, 1))
+    status = gpu.Groth16Verifier.verify_batch(proofs, vk, inputs)
+    _, st_c = ref_cpu.groth16_verify_batch(vk, proofs, inputs, threads=os.cpu_count() or 1)
+    assert (status == st_c).all(), [(klass[i], int(status[i]), int(st_c[i])) for i in np.nonzero(status != st_c)[0][:8]]
+    for i, k in enumerate(klass):
+        want_in = k == "in G2"
+        assert (status[i] != gpu.PANIC_NOT_IN_SUBGROUP) == want_in, (k, int(status[i]))
+        if want_in:
+            assert status[i] == gpu.OK_FALSE  # a valid proof whose B was replaced
+    check = [i for i, k in enumerate(klass) if k != "random"] + list(range(0, 3800, 19))
+    for i in check:
+        assert bo.g2_in_subgroup(points[i]) == (klass[i] == "in G2"), klass[i]
+    # the same points in a batch small enough for the fused small-batch kernel (another launch shape)
+    sub = np.array([i for i, k in enumerate(klass) if k != "random"][:96] + list(range(32)))
+    assert (gpu.Groth16Verifier.verify_batch(proofs[sub], vk, inputs[sub]) == status[sub]).all()
+
+
+def test_bundled_groth16_raw_proofs_through_the_decoder(gpu):
+    """The reference repo holds 4 Groth16 raw proofs (324 bytes) but not their VK: under a trapdoor VK
+    the device decoder must accept A, B, C (on curve, B in G2) and the verdict must be the oracle's Ok(false)."""
+    fx = load_json("fixtures.json")
+    td = bo.Groth16Trapdoor(3, 2, 0)
+    vk = td.vk_bytes()
+    proofs, inputs = [], []
+    for prog in ("fibonacci", "is-prime", "sha2", "tendermint"):
+        f = fx[f"{prog}_groth16"]
+        raw = bytes.fromhex(f["raw_proof"])
+        assert len(raw) == 324
+        proofs.append(raw), inputs.append([int(s) for s in f["inputs"]])
+    status = gpu.Groth16Verifier.verify_batch(proofs, vk, inputs)
+    for pr, xs, st in zip(proofs, inputs, status):
+        assert gpu.status_name(st) == oracle_groth16_status(pr, vk, xs) == "OK_FALSE"
+
+
+@pytest.mark.parametrize("n", [100, 30000, 60000, 240000])
+def test_failed_proofs_inside_warps_every_launch_shape(gpu, n):
+    """Malformed and rejected proofs scattered inside warps of well-formed ones, for every launch shape (32-thread
+    blocks, 128 x 2, 448 two-launch, 384 two-launch): the pairing kernels contain block-wide barriers, so a failed proof
+    must neither hang its block nor disturb its neighbours.  Every status as expected."""
+    td = bo.Groth16Trapdoor(2024, 2, 0)
+    vk, proofs, inputs, expected = gpu.groth16_synth(2024, n)
+    assert vk == td.vk_bytes()
+    suite = [c for c in groth16_malformed_suite(td) if len(c[2]) == 2 and len(c[1]) == 256]
+    rng = np.random.default_rng(n)
+    pos = rng.choice(n, size=min(n // 3, 40 * len(suite)), replace=False)
+    proofs, inputs, expected = proofs.copy(), inputs.copy(), expected.copy()
+    names = {gpu.status_name(s): s for s in range(0, 24)}
+    for j, p in enumerate(pos):
+        name, pb, xs, want = suite[j % len(suite)]
+        proofs[p] = np.frombuffer(pb, np.uint8)
+        inputs[p] = gpu.fr_to_be(xs)
+        expected[p] = names[want]
+    status = gpu.Groth16Verifier.verify_batch(proofs, vk, inputs)
+    bad = np.nonzero(status != expected)[0]
+    assert bad.size == 0, [(int(i), gpu.status_name(status[i]), gpu.status_name(expected[i])) for i in bad[:8]]

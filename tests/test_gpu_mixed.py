@@ -1,0 +1,60 @@
+"""GPU parity: mixed Groth16 + PlonK batches through bn254v_verify_many (BASELINE.json configs[4] shape) and the
+library's VK cache."""
+import os
+
+import numpy as np
+import pytest
+
+import bn254_oracle as bo
+from helpers import plonk_vk_bytes
+
+pytestmark = pytest.mark.gpu
+
+
+def test_vk_cache_is_keyed_by_vk_hash(gpu):
+    gpu.vk_cache_clear()
+    assert gpu.vk_cache_size() == 0
+    tds = [bo.Groth16Trapdoor(s, 2, 0) for s in (41, 42)]
+    for rep in range(3):
+        for td in tds:
+            pb, xs, valid = td.proof(1)
+            assert gpu.Groth16Verifier.verify(pb, td.vk_bytes(), xs) is valid
+    assert gpu.vk_cache_size() == 2
+    gnark = type("V", (gpu.Groth16Verifier,), {"sign_mode": 1})
+    pb, xs, _ = tds[0].proof(0, corrupt=False)
+    assert gnark.verify(pb, tds[0].vk_bytes(), xs) is False  # same bytes, other sign convention: its own handle
+    assert gpu.vk_cache_size() == 3
+    gpu.PlonkVerifier.verify_batch(np.zeros((1, 904), np.uint8), plonk_vk_bytes(), np.zeros((1, 2, 32), np.uint8))
+    assert gpu.vk_cache_size() == 4
+    gpu.vk_cache_clear()
+    assert gpu.vk_cache_size() == 0
+    pb, xs, valid = tds[1].proof(2)
+    assert gpu.Groth16Verifier.verify(pb, tds[1].vk_bytes(), xs) is valid  # rebuilt after the clear
+
+
+def test_unparsable_vk_in_a_mixed_batch(gpu):
+    td = bo.Groth16Trapdoor(9, 2, 0)
+    pb, xs, valid = td.proof(0, corrupt=False)
+    items = [("groth16", pb, td.vk_bytes(), xs), ("groth16", pb, td.vk_bytes()[:100], xs),
+             ("plonk", pb, td.vk_bytes(), xs), ("groth16", pb, td.vk_bytes(), [xs[0]])]
+    st = gpu.verify_many(items)
+    assert [gpu.status_name(s) for s in st] == ["OK_TRUE", "PANIC_VK_PARSE", "PANIC_VK_PARSE", "ERR_PREPARE_INPUTS"]
+
+
+def test_mixed_batch_config5_parity(gpu):
+    """2^16 items: 2^15 trapdoor Groth16 proofs (50 % corrupted) interleaved one-to-one with 2^15 PlonK proofs (bundled
+    fixtures replicated, 50 % mutated), through ONE bn254v_verify_many call.  Every status equals the generators'
+    expectation, and a strided sample of 512 items equals the C++ oracle's verdict for the same item."""
+    import ref_cpu
+    import workloads
+    half = 1 << 15
+    vk_g, pr_g, in_g, exp_g = gpu.groth16_synth(777, half)
+    pr_p, in_p, rnd_p, exp_p = workloads.plonk_workload(half, seed=9)
+    vk_p = plonk_vk_bytes()
+    status = gpu.verify_mixed_arrays(vk_g, pr_g, in_g, vk_p, pr_p, in_p, rnd_p)
+    assert (status[0::2] == exp_g).all() and (status[1::2] == exp_p).all()
+    idx = np.arange(0, half, half // 256)
+    _, st_c = ref_cpu.groth16_verify_batch(vk_g, pr_g[idx], in_g[idx], threads=os.cpu_count() or 1)
+    assert (status[0::2][idx] == st_c).all()
+    _, st_c = ref_cpu.plonk_verify_batch(vk_p, pr_p[idx], in_p[idx], rnd_p[idx], threads=os.cpu_count() or 1)
+    assert (status[1::2][idx] == st_c).all()

@@ -58,3 +58,36 @@ def test_full_size_config4_against_cpp_oracle(gpu):
     _, ml, gt = gpu.pairing_product_batch(g1[idx], g2[idx], 4, want_values=True)
     _, one_c, ml_c, gt_c = ref_cpu.pairing_product_batch(g1[idx], g2[idx], 4, threads=os.cpu_count() or 1)
     assert (ml == ml_c).all() and (gt == gt_c).all() and (one_c == expected[idx]).all()
+
+
+def test_identity_pairs_are_skipped(gpu):
+    """A pair with an identity member (all-zero bytes) is skipped as in substrate-bn's pairing_batch: Miller and GT
+    values are those of the remaining pairs (bit-exact against the oracle); a set of identities only gives 1."""
+    n, k = 64, 4
+    g1, g2, _ = gpu.pairing_synth(99, n, k=k)
+    g1, g2 = g1.copy(), g2.copy()
+    rng = np.random.default_rng(5)
+    masks = []
+    for i in range(n):
+        z1 = set(np.nonzero(rng.integers(0, 3, k) == 0)[0].tolist()) if i % 4 else set()
+        z2 = set(np.nonzero(rng.integers(0, 4, k) == 0)[0].tolist()) if i % 4 else set()
+        if i == 5:
+            z1, z2 = {0, 1, 2, 3}, set()
+        if i == 6:
+            z1, z2 = {0, 2}, {1, 3}
+        for j in z1:
+            g1[i, j] = 0
+        for j in z2:
+            g2[i, j] = 0
+        masks.append((z1, z2))
+    is_one, ml, gt = gpu.pairing_product_batch(g1, g2, k, want_values=True)
+    for i in list(range(12)) + [20, 33, 47, 63]:
+        z1, z2 = masks[i]
+        pairs = [(None if j in z1 else bo.uncompressed_bytes_to_g1_point(g1[i, j].tobytes()),
+                  None if j in z2 else bo.uncompressed_bytes_to_g2_point(g2[i, j].tobytes())) for j in range(k)]
+        m = bo.miller_product(pairs)
+        m = bo.FP12_ONE if m is None else m
+        e = bo.final_exponentiation(m)
+        assert bo.fp12_to_bytes(m) == ml[i].tobytes() and bo.fp12_to_bytes(e) == gt[i].tobytes(), (i, z1, z2)
+        assert bool(is_one[i]) == (e == bo.FP12_ONE)
+    assert is_one[5] == 1 and is_one[6] == 1

@@ -141,3 +141,41 @@ def test_mixed_batch_over_several_vks(gpu):
     want.append(1)
     st = gpu.verify_many(items)
     assert st.tolist() == want
+
+
+def test_other_circuit_shapes(gpu):
+    """VK shapes other than the bundled one (nQcp = 1, nPub = 2; BN_MAX_QCP / BN_MAX_PLONK_PUBLIC in plonk.cuh): no
+    BSB22 commitment / one public input, two commitments / three inputs, three commitments.  Proofs derived from a
+    bundled one with claimed[0] solved (helpers.plonk_shape_variant): the whole path runs (both MSM rounds with the other
+    term counts, the KZG transcript over more digests) and every intermediate equals the oracle's."""
+    import plonk_oracle as po
+    from helpers import plonk_shape_variant
+    for nq, npub in ((0, 1), (2, 3), (3, 2)):
+        vkb, pr, xs = plonk_shape_variant(nq, npub)
+        d = {}
+        with pytest.raises(po.PlonkError) as e:
+            po.plonk_verifier_verify(pr, vkb, xs, rnd=4242, debug=d)
+        assert e.value.kind == "PAIRING_CHECK_FAILED"
+        status, dbg = gpu.PlonkVerifier.verify_batch([pr] * 3, vkb, [xs] * 3, rnd=[4242] * 3, debug=True)
+        assert (status == gpu.ERR_PAIRING_CHECK_FAILED).all()
+        for j, nm in enumerate(["gamma", "beta", "alpha", "zeta", "kzg_gamma", "pi", "const_lin"]):
+            assert dbg.fr[1, j].tobytes() == d[nm].to_bytes(32, "big"), (nq, npub, nm)
+        if nq:
+            assert dbg.fr[1, 7].tobytes() == d["hashed_bsb22"][0].to_bytes(32, "big")
+        assert dbg.g1[1, 0].tobytes() == bo.g1_to_bytes(d["lin_digest"])
+        assert dbg.g1[1, 1].tobytes() == bo.g1_to_bytes(d["folded_digest"])
+        assert dbg.g1[1, 2].tobytes() == bo.g1_to_bytes(d["pair_g1"][0])
+        assert dbg.g1[1, 3].tobytes() == bo.g1_to_bytes(d["pair_g1"][1])
+        assert dbg.miller[1].tobytes() == bo.fp12_to_bytes(d["miller"]) and dbg.gt[1].tobytes() == bo.fp12_to_bytes(d["gt"])
+
+
+def test_library_drawn_batch_opening_scalars(gpu):
+    """rnd = None is the production path: the library draws the scalars of kzg::batch_verify_multi_points from the OS
+    CSPRNG (kzg.rs:149-154).  Verdicts do not depend on them; the pairing inputs do, so two calls differ."""
+    vk = plonk_vk_bytes()
+    pr, xs = plonk_fixture("sha2")
+    st1, d1 = gpu.PlonkVerifier.verify_batch([pr] * 4, vk, [xs] * 4, debug=True)
+    st2, d2 = gpu.PlonkVerifier.verify_batch([pr] * 4, vk, [xs] * 4, debug=True)
+    assert (st1 == gpu.OK_TRUE).all() and (st2 == gpu.OK_TRUE).all()
+    seen = {d.g1[i, 2].tobytes() for d in (d1, d2) for i in range(4)}
+    assert len(seen) == 8

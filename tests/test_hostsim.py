@@ -308,3 +308,62 @@ def test_glv_windowed_scalar_multiplication(hs):
                 assert ok == 0
             else:
                 assert ok == 1 and out.raw == bo.g1_to_bytes(want), hex(k)
+
+
+def _plonk_debug_matches_oracle(d, g1, fr, ml, gt):
+    """canonical debug bytes (bn254v_debug layout) against the oracle's debug dict"""
+    for j, nm in enumerate(["gamma", "beta", "alpha", "zeta", "kzg_gamma", "pi", "const_lin"]):
+        assert fr[32 * j:32 * j + 32] == d[nm].to_bytes(32, "big"), nm
+    if d["hashed_bsb22"]:
+        assert fr[224:256] == d["hashed_bsb22"][0].to_bytes(32, "big")
+    assert g1[0:64] == bo.g1_to_bytes(d["lin_digest"]) and g1[64:128] == bo.g1_to_bytes(d["folded_digest"])
+    assert g1[128:192] == bo.g1_to_bytes(d["pair_g1"][0]) and g1[192:256] == bo.g1_to_bytes(d["pair_g1"][1])
+    assert ml == bo.fp12_to_bytes(d["miller"]) and gt == bo.fp12_to_bytes(d["gt"])
+
+
+def test_plonk_other_circuit_shapes(hs):
+    """VK shapes other than the bundled one (nQcp = 1, nPub = 2): no BSB22 commitment / one public input, two
+    commitments / three public inputs, three commitments.  The proofs are derived from a bundled one with claimed[0]
+    solved (helpers.plonk_shape_variant), so the whole path runs and every intermediate is compared with the oracle."""
+    import plonk_oracle as po
+    from helpers import plonk_shape_variant
+    _hs_plonk(hs)
+    for nq, npub in ((0, 1), (2, 3), (3, 2)):
+        vkb, pr, xs = plonk_shape_variant(nq, npub)
+        d = {}
+        with pytest.raises(po.PlonkError) as e:
+            po.plonk_verifier_verify(pr, vkb, xs, rnd=4242, debug=d)
+        assert e.value.kind == "PAIRING_CHECK_FAILED"
+        vk = hs.hs_plonk_vk_new(vkb, len(vkb))
+        assert vk
+        inputs = b"".join(x.to_bytes(32, "big") for x in xs)
+        g1, fr, ml, gt = (ctypes.create_string_buffer(n) for n in (256, 256, 384, 384))
+        st = hs.hs_plonk_verify(vk, pr, len(pr), inputs, npub, (4242).to_bytes(32, "big"), g1, fr, ml, gt)
+        assert st == 8, (nq, npub, st)  # ERR_PAIRING_CHECK_FAILED
+        _plonk_debug_matches_oracle(d, g1.raw, fr.raw, ml.raw, gt.raw)
+        hs.hs_plonk_vk_free(vk)
+
+
+def test_pairing_product_skips_identity_pairs(hs):
+    """bn::pairing_batch skips a pair with an identity member (all-zero bytes here): the Miller and GT values are
+    those of the remaining pairs; a set of identities only gives 1."""
+    c = [x for x in load_json("pairing_golden.json") if x["k"] == 3][0]
+    g1, g2 = bytearray(bytes.fromhex(c["g1"])), bytearray(bytes.fromhex(c["g2"]))
+    pts = [(bo.uncompressed_bytes_to_g1_point(bytes(g1[64 * j:64 * j + 64])),
+            bo.uncompressed_bytes_to_g2_point(bytes(g2[128 * j:128 * j + 128]))) for j in range(3)]
+    for zero_g1, zero_g2 in (({1}, set()), (set(), {0}), ({0}, {2}), ({0, 1, 2}, set()), ({0, 1}, {2})):
+        a, b = bytearray(g1), bytearray(g2)
+        pairs = []
+        for j in range(3):
+            if j in zero_g1:
+                a[64 * j:64 * j + 64] = bytes(64)
+            if j in zero_g2:
+                b[128 * j:128 * j + 128] = bytes(128)
+            pairs.append((None if j in zero_g1 else pts[j][0], None if j in zero_g2 else pts[j][1]))
+        m = bo.miller_product(pairs)
+        m = bo.FP12_ONE if m is None else m
+        want_gt = bo.final_exponentiation(m)
+        ml, gt = ctypes.create_string_buffer(384), ctypes.create_string_buffer(384)
+        one = hs.hs_pairing_product(3, bytes(a), bytes(b), ml, gt)
+        assert ml.raw == bo.fp12_to_bytes(m) and gt.raw == bo.fp12_to_bytes(want_gt), (zero_g1, zero_g2)
+        assert bool(one) == (want_gt == bo.FP12_ONE)

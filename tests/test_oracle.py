@@ -200,3 +200,24 @@ def test_ate_endpoint_subgroup_test_is_exact():
 
     assert gcd(norm(6 * x + 2, 1, -1, 1), n_curve) == r
     assert gcd(norm(x + 1, x, x, -2 * x), n_curve) == r
+
+
+def test_miller_chain_has_no_exceptional_step_on_the_twist():
+    """The GPU reads G2 membership off the end point of the Miller loop's own point chain (csrc/pairing_body.inc,
+    ate_endpoint_in_g2) for EVERY point of E'(Fq2), so the step formulas must not degenerate on points outside G2
+    either.  Integer fact: with s_i the scalar prefixes of the 64-digit NAF chain, no point Q != O of E'(Fq2) has
+    [s_i]Q = O before a doubling, a 2-torsion running point, or [s_i -+ 1]Q = O at an addition of +-Q, because every
+    such scalar is coprime to #E'(Fq2) = r (2p - r)."""
+    from math import gcd
+    n_twist = bo.R * (2 * bo.P - bo.R)
+    s = 1
+    for d in bo.ATE_NAF:
+        assert gcd(s, n_twist) == 1 and gcd(2 * s, n_twist) == 1
+        s *= 2
+        if d:
+            e = 1 if d == 1 else -1
+            assert gcd(s - e, n_twist) == 1 and gcd(s + e, n_twist) == 1
+            s += e
+    assert s == 6 * bo.X + 2
+    for ell in (10069, 5864401, 1875725156269):  # the small prime factors of the cofactor
+        assert (2 * bo.P - bo.R) % ell == 0
