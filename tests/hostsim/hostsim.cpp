@@ -160,6 +160,33 @@ int hs_plonk_verify(void* vk, const uint8_t* proof, uint32_t len, const uint8_t*
   PlonkDebug dbg{g1, fr, miller, gt};
   return plonk_verify_one(*(PlonkVkDev*)vk, proof, len, inputs, n_inputs, rnd, dbg);
 }
+// limb multiply-adds of each stage of the staged PlonK path (the five kernels of k_plonk.cu): out[0..4] = stage A,
+// terms 0, stage C, terms 1, stage E.  Returns the final status (a proof rejected in stage A leaves out[1..4] = 0).
+int hs_plonk_stage_macs(void* vkp, const uint8_t* pr, uint32_t len, const uint8_t* inputs, int n_inputs,
+                        const uint8_t* rnd, unsigned long long* out) {
+  const PlonkVkDev& vk = *(PlonkVkDev*)vkp;
+  PlonkDebug dbg{nullptr, nullptr, nullptr, nullptr};
+  for (int i = 0; i < 5; i++) out[i] = 0;
+#ifdef BN254_COUNT_MULS
+  PlonkWork w;
+  fe_mac_counter() = 0;
+  int st = plonk_stage_a(w, vk, pr, len, inputs, n_inputs, dbg);
+  out[0] = fe_mac_counter(), fe_mac_counter() = 0;
+  if (st != BN254V_OK_TRUE) return st;
+  for (int t = 0; t < vk.n_qcp + 10; t++) plonk_term(w, vk, pr, 0, t);
+  out[1] = fe_mac_counter(), fe_mac_counter() = 0;
+  st = plonk_stage_c(w, vk, pr, rnd, dbg);
+  out[2] = fe_mac_counter(), fe_mac_counter() = 0;
+  if (st != BN254V_OK_TRUE) return st;
+  for (int t = 0; t < vk.n_qcp + 10; t++) plonk_term(w, vk, pr, 1, t);
+  out[3] = fe_mac_counter(), fe_mac_counter() = 0;
+  st = plonk_stage_e(w, vk, pr, dbg);
+  out[4] = fe_mac_counter(), fe_mac_counter() = 0;
+  return st;
+#else
+  return -1;
+#endif
+}
 void hs_fp2_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {  // 16 words each: c0 | c1 (Montgomery)
   Fp2 x, y;
   memcpy(x.c0.v, a, 32), memcpy(x.c1.v, a + 8, 32), memcpy(y.c0.v, b, 32), memcpy(y.c1.v, b + 8, 32);

@@ -57,18 +57,30 @@ def main(write=True):
         hs.hs_mul_count(1)
         hs.hs_pairing_product(c["k"], bytes.fromhex(c["g1"]), bytes.fromhex(c["g2"]), None, None)
         out["pairing_product_k%d_macs" % c["k"]] = hs.hs_mul_count(1)
-    # PlonK: full path (valid proof) and early reject
+    # PlonK: full path (valid proof) per stage of the staged GPU path, and early reject.  The VK-constant bases go
+    # through the fixed-base window tables, exactly as on the device (hs_plonk_vk_add_tables) -- without them the
+    # 8 + nQcp VK terms would be counted as variable-base multiplications the GPU never executes.
     vkb = plonk_vk_bytes()
     pv = hs.hs_plonk_vk_new(vkb, len(vkb))
+    hs.hs_plonk_vk_add_tables.argtypes = [ctypes.c_void_p]
+    hs.hs_plonk_vk_add_tables(pv)
+    hs.hs_plonk_stage_macs.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_int,
+                                       ctypes.c_char_p, ctypes.POINTER(ctypes.c_ulonglong)]
     pr, xs = plonk_fixture("fibonacci")
     inputs = b"".join(x.to_bytes(32, "big") for x in xs)
     hs.hs_mul_count(1)
     assert hs.hs_plonk_verify(pv, pr, len(pr), inputs, 2, (77).to_bytes(32, "big"), None, None, None, None) == 0
     out["plonk_full_path_macs"] = hs.hs_mul_count(1)
     out["plonk_full_path_mul"] = out["plonk_full_path_macs"] // 136
+    stages = (ctypes.c_ulonglong * 5)()
+    assert hs.hs_plonk_stage_macs(pv, pr, len(pr), inputs, 2, (77).to_bytes(32, "big"), stages) == 0
+    out["plonk_stage_macs"] = {k: int(v) for k, v in zip(("stage_a", "terms0", "stage_c", "terms1", "stage_e"), stages)}
+    assert sum(out["plonk_stage_macs"].values()) == out["plonk_full_path_macs"]
     bad = [m for m in load_json("plonk_mutations.json") if m["program"] == "fibonacci" and m["mutation"] == "claimed0+1"][0]
+    hs.hs_mul_count(1)
     hs.hs_plonk_verify(pv, bytes.fromhex(bad["raw_proof"]), 904, inputs, 2, (77).to_bytes(32, "big"), None, None, None, None)
-    out["plonk_early_reject_mul"] = hs.hs_mul_count(1) // 136
+    out["plonk_early_reject_macs"] = hs.hs_mul_count(1)
+    out["plonk_early_reject_mul"] = out["plonk_early_reject_macs"] // 136
     if write:
         json.dump(out, open(os.path.join(ROOT, "profiles", "workcount.json"), "w"), indent=1)
     return out
