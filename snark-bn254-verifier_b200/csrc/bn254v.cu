@@ -124,6 +124,51 @@ struct DevBuf {  // RAII scratch allocation on the current device (returned to t
   T* as() { return (T*)p; }
 };
 
+// Pinned host staging (mixed batches gather their groups into it so that the H2D copies run at full PCIe speed and
+// asynchronously); cudaHostAlloc costs tens of milliseconds, so the blocks are kept for the life of the library.
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  ~PinnedBuf() {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_pinned().push_back(Block{p, cap, -1});
+  }
+  static std::vector<Block>& g_pinned() {
+    static std::vector<Block> v;
+    return v;
+  }
+  cudaError_t reserve(size_t n) {
+    if (!n) n = 1;
+    if (cap >= n) return cudaSuccess;
+    {
+      std::lock_guard<std::mutex> lk(g_pool_mu);
+      if (p) g_pinned().push_back(Block{p, cap, -1});
+      p = nullptr, cap = 0;
+      auto& v = g_pinned();
+      int best = -1;
+      for (int i = 0; i < (int)v.size(); i++)
+        if (v[i].cap >= n && (best < 0 || v[i].cap < v[best].cap)) best = i;
+      if (best >= 0) {
+        p = v[best].p, cap = v[best].cap;
+        v.erase(v.begin() + best);
+        return cudaSuccess;
+      }
+    }
+    cudaError_t e = cudaHostAlloc(&p, n, cudaHostAllocPortable);
+    if (e == cudaSuccess) cap = n;
+    else p = nullptr;
+    return e;
+  }
+  static void release_all() {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (auto& b : g_pinned()) cudaFreeHost(b.p);
+    g_pinned().clear();
+  }
+  template <class T>
+  T* as() { return (T*)p; }
+};
+
 // Declared AFTER the per-device buffers of a batch call, so that it is destroyed BEFORE them on every exit path --
 // including the early returns of CU() -- and no asynchronous copy still uses caller memory, or a scratch block that is
 // about to go back to the pool, when the function returns.
@@ -299,6 +344,7 @@ void bn254v_shutdown(void) {
     cudaStreamDestroy(d.stream);
     for (auto& ev : d.ev) cudaEventDestroy(ev);
   }
+  PinnedBuf::release_all();
   g_devs.clear();
   g_inited = false;
 }
@@ -685,11 +731,35 @@ int bn254v_verify_many(const bn254v_item* items, size_t n, int sign_mode, const 
   std::vector<Group> groups;
   std::map<std::string, int> by_key;                                     // (kind, n_inputs, vk hash) -> group
   std::map<std::pair<const uint8_t*, size_t>, std::string> key_of_ptr;    // identical VK pointers are hashed once
+  struct Recent {
+    const uint8_t* vk;
+    size_t vk_len;
+    int kind, n_inputs, group;
+  };
+  Recent recent[8];
+  int n_recent = 0;
   for (size_t i = 0; i < n; i++) {
     const bn254v_item& it = items[i];
     if ((it.kind != BN254V_KIND_GROTH16 && it.kind != BN254V_KIND_PLONK) || !it.vk || (it.proof_len && !it.proof) ||
         it.n_inputs < 0 || (it.n_inputs && !it.inputs_be))
       return fail(BN254V_E_BAD_ARG, "item %zu: bad argument", i);
+    // fast path: the (VK pointer, kind, n_inputs) combinations seen most recently (a few per call in practice)
+    int hit = -1;
+    for (int q = 0; q < n_recent; q++)
+      if (recent[q].vk == it.vk && recent[q].vk_len == it.vk_len && recent[q].kind == it.kind &&
+          recent[q].n_inputs == it.n_inputs) {
+        hit = recent[q].group;
+        break;
+      }
+    if (hit >= 0) {
+      Group& gr = groups[hit];
+      if (it.proof_len != gr.stride) {
+        gr.ragged = true;
+        if (it.proof_len > gr.stride) gr.stride = it.proof_len;
+      }
+      gr.pos.push_back(i);
+      continue;
+    }
     auto pk = std::make_pair(it.vk, it.vk_len);
     auto f = key_of_ptr.find(pk);
     if (f == key_of_ptr.end()) f = key_of_ptr.emplace(pk, vk_key(it.kind, it.kind ? 0 : sign_mode, it.vk, it.vk_len)).first;
@@ -712,45 +782,102 @@ int bn254v_verify_many(const bn254v_item* items, size_t n, int sign_mode, const 
     if (!gr.pos.empty() && it.proof_len != gr.stride) gr.ragged = true;
     if (it.proof_len > gr.stride) gr.stride = it.proof_len;
     gr.pos.push_back(i);
+    recent[n_recent < 8 ? n_recent++ : (i & 7)] = Recent{it.vk, it.vk_len, it.kind, it.n_inputs, g->second};
   }
+  // A group is cut into chunks; while the devices verify chunk k (a helper thread inside the synchronous batch entry
+  // point), the host cores gather chunk k + 1 into the other pinned staging set: the gather of a large mixed batch (GBs)
+  // is hidden behind the kernels.
   const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  const size_t CH = (size_t)1 << 17;
+  struct Task {
+    Group* gr;
+    size_t first, m;
+  };
+  std::vector<Task> tasks;
   for (Group& gr : groups) {
-    const size_t m = gr.pos.size();
     if (!gr.vk) {
       for (size_t j : gr.pos) status[j] = BN254V_PANIC_VK_PARSE;
       continue;
     }
+    for (size_t f = 0; f < gr.pos.size(); f += CH) tasks.push_back(Task{&gr, f, std::min(CH, gr.pos.size() - f)});
+  }
+  struct Stage {
+    PinnedBuf proofs, inputs, rnd, st, lens;
+    Task t{nullptr, 0, 0};
+    bool has_rnd = false;
+    int rc = 0;
+    std::string err;
+  };
+  Stage stages[2];
+  auto pack = [&](Stage& sg, const Task& t) -> int {
+    Group& gr = *t.gr;
     const size_t in_bytes = (size_t)32 * gr.n_inputs;
-    std::vector<uint8_t> proofs(m * gr.stride), inputs(m * in_bytes + 1), st(m), rnd;
-    std::vector<uint32_t> lens(gr.ragged ? m : 0);
-    if (gr.kind == BN254V_KIND_PLONK && rnd_be) rnd.resize(m * 32);
-    auto pack = [&](size_t a, size_t b) {
+    sg.t = t;
+    sg.has_rnd = gr.kind == BN254V_KIND_PLONK && rnd_be;
+    CU(sg.proofs.reserve(t.m * gr.stride));
+    CU(sg.inputs.reserve(t.m * in_bytes + 1));
+    CU(sg.st.reserve(t.m));
+    if (gr.ragged) CU(sg.lens.reserve(t.m * 4));
+    if (sg.has_rnd) CU(sg.rnd.reserve(t.m * 32));
+    uint8_t *pp = sg.proofs.as<uint8_t>(), *pi = sg.inputs.as<uint8_t>(), *pr = sg.rnd.as<uint8_t>();
+    uint32_t* pl = sg.lens.as<uint32_t>();
+    auto work = [&](size_t a, size_t b) {
       for (size_t j = a; j < b; j++) {
-        const bn254v_item& it = items[gr.pos[j]];
-        if (it.proof_len) memcpy(&proofs[j * gr.stride], it.proof, it.proof_len);
-        if (it.proof_len < gr.stride) memset(&proofs[j * gr.stride + it.proof_len], 0, gr.stride - it.proof_len);
-        if (in_bytes) memcpy(&inputs[j * in_bytes], it.inputs_be, in_bytes);
-        if (gr.ragged) lens[j] = (uint32_t)it.proof_len;
-        if (!rnd.empty()) memcpy(&rnd[j * 32], rnd_be + 32 * gr.pos[j], 32);
+        const size_t pos = gr.pos[t.first + j];
+        const bn254v_item& it = items[pos];
+        if (it.proof_len) memcpy(pp + j * gr.stride, it.proof, it.proof_len);
+        if (it.proof_len < gr.stride) memset(pp + j * gr.stride + it.proof_len, 0, gr.stride - it.proof_len);
+        if (in_bytes) memcpy(pi + j * in_bytes, it.inputs_be, in_bytes);
+        if (gr.ragged) pl[j] = (uint32_t)it.proof_len;
+        if (sg.has_rnd) memcpy(pr + j * 32, rnd_be + 32 * pos, 32);
       }
     };
-    if (m < 4096 || hw == 1) {
-      pack(0, m);
-    } else {  // the gather is a few GB at 2^22 items: spread it over the host cores
+    if (t.m < 4096 || hw == 1) {
+      work(0, t.m);
+    } else {
       std::vector<std::thread> th;
-      for (unsigned t = 0; t < hw; t++) th.emplace_back(pack, m * t / hw, m * (t + 1) / hw);
-      for (auto& t : th) t.join();
+      for (unsigned k = 0; k < hw; k++) th.emplace_back(work, t.m * k / hw, t.m * (k + 1) / hw);
+      for (auto& x : th) x.join();
     }
+    return 0;
+  };
+  auto run = [&](Stage* sg) {
+    Group& gr = *sg->t.gr;
     if (gr.kind == BN254V_KIND_GROTH16)
-      rc = bn254v_groth16_verify_batch(gr.vk, proofs.data(), gr.stride, gr.ragged ? lens.data() : nullptr, inputs.data(),
-                                       gr.n_inputs, m, st.data(), nullptr);
+      sg->rc = bn254v_groth16_verify_batch(gr.vk, sg->proofs.as<uint8_t>(), gr.stride,
+                                           gr.ragged ? sg->lens.as<uint32_t>() : nullptr, sg->inputs.as<uint8_t>(),
+                                           gr.n_inputs, sg->t.m, sg->st.as<uint8_t>(), nullptr);
     else
-      rc = bn254v_plonk_verify_batch(gr.vk, proofs.data(), gr.stride, gr.ragged ? lens.data() : nullptr, inputs.data(),
-                                     gr.n_inputs, rnd.empty() ? nullptr : rnd.data(), m, st.data(), nullptr);
-    if (rc) return rc;
-    for (size_t j = 0; j < m; j++) status[gr.pos[j]] = st[j];
+      sg->rc = bn254v_plonk_verify_batch(gr.vk, sg->proofs.as<uint8_t>(), gr.stride,
+                                         gr.ragged ? sg->lens.as<uint32_t>() : nullptr, sg->inputs.as<uint8_t>(),
+                                         gr.n_inputs, sg->has_rnd ? sg->rnd.as<uint8_t>() : nullptr, sg->t.m,
+                                         sg->st.as<uint8_t>(), nullptr);
+    if (sg->rc) sg->err = g_err;  // (thread-local in the helper thread)
+  };
+  auto collect = [&](Stage& sg) -> int {
+    if (sg.rc) return fail(sg.rc, "%s", sg.err.c_str());
+    const uint8_t* st = sg.st.as<uint8_t>();
+    for (size_t j = 0; j < sg.t.m; j++) status[sg.t.gr->pos[sg.t.first + j]] = st[j];
+    return 0;
+  };
+  std::thread worker;
+  int result = 0;
+  for (size_t k = 0; k < tasks.size() && !result; k++) {
+    Stage& cur = stages[k & 1];
+    result = pack(cur, tasks[k]);
+    if (worker.joinable()) {
+      worker.join();
+      int r2 = collect(stages[(k - 1) & 1]);
+      if (!result) result = r2;
+    }
+    if (!result) worker = std::thread(run, &cur);
   }
-  return BN254V_SUCCESS;
+  if (worker.joinable()) {
+    worker.join();
+    int r2 = collect(stages[(tasks.size() - 1) & 1]);
+    if (!result) result = r2;
+  }
+  return result;
 }
 
 // ---- device-resident batches (bn254v_bench.h) ----------------------------------------------------

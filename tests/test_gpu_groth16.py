@@ -167,7 +167,7 @@ def test_g2_membership_hardening(gpu):
     vk = td.vk_bytes()
     pb, xs, _ = td.proof(0, corrupt=False)
     points, klass = [], []
-    for _ in range(3800):
+    for _ in range(3840):
         points.append(random_twist_point(rng)), klass.append("random")
     small = {ell: [twist_point_of_order(ell, rng) for _ in range(24)] for ell in TWIST_COFACTOR_SMALL_PRIMES}
     for ell, pts in small.items():
@@ -197,7 +197,7 @@ def test_g2_membership_hardening(gpu):
         assert (status[i] != gpu.PANIC_NOT_IN_SUBGROUP) == want_in, (k, int(status[i]))
         if want_in:
             assert status[i] == gpu.OK_FALSE  # a valid proof whose B was replaced
-    check = [i for i, k in enumerate(klass) if k != "random"] + list(range(0, 3800, 19))
+    check = [i for i, k in enumerate(klass) if k != "random"] + list(range(0, 3840, 19))
     for i in check:
         assert bo.g2_in_subgroup(points[i]) == (klass[i] == "in G2"), klass[i]
     # the same points in a batch small enough for the fused small-batch kernel (another launch shape)
