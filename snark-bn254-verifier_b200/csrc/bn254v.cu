@@ -788,7 +788,7 @@ int bn254v_verify_many(const bn254v_item* items, size_t n, int sign_mode, const 
   // point), the host cores gather chunk k + 1 into the other pinned staging set: the gather of a large mixed batch (GBs)
   // is hidden behind the kernels.
   const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-  const size_t CH = (size_t)1 << 17;
+  const size_t CH = (size_t)1 << 18;
   struct Task {
     Group* gr;
     size_t first, m;
