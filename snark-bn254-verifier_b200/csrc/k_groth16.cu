@@ -5,7 +5,10 @@
 // Every thread of a block -- spare threads of the last block and proofs that failed validation included -- runs the
 // same sequence of Miller-loop / exponentiation iterations, because those contain block-wide phase barriers
 // (field.cuh, BN_PHASE_SYNC): nothing returns before the last barrier.
+#include <stdlib.h>
+
 #include "kernels.h"
+#include "trio.cuh"
 
 namespace bn254 {
 namespace {
@@ -81,6 +84,16 @@ namespace launch {
 // 147 blocks on 148 SMs); 384 threads x 168 registers is 9 % faster per proof (a 16 K-register SMSP holds 3 warps at 168
 // or 4 at 128) but 2^16 proofs do not fit one wave of it, so it is used once there are several waves; small batches use
 // smaller blocks so that every SM gets work.
+size_t trio_max_items(int sm_count) {
+  static long forced = -2;
+  if (forced == -2) {
+    const char* e = getenv("BN254V_TRIO_MAX");
+    forced = e ? atol(e) : -1;
+  }
+  if (forced >= 0) return (size_t)forced;
+  return (size_t)sm_count * 128;  // below ~one warp per SM sub-partition with one item per thread
+}
+
 int pick_shape(size_t m, int sm_count) {
   if (m >= (size_t)sm_count * 384 * 4) return SHAPE_384;
   if (m >= (size_t)sm_count * 448 * 3 / 4) return SHAPE_448;

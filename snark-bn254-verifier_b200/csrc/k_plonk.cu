@@ -5,6 +5,7 @@
 // `list` holds the indices of the proofs that are still alive after stage A (early rejects cost nothing further);
 // a slot is set to -(i + 1) when stage C ends the proof.
 #include "kernels.h"
+#include "trio.cuh"
 
 namespace bn254 {
 namespace {
@@ -86,6 +87,49 @@ __global__ void __launch_bounds__(TPB, 1)
   if (live) status[i] = (uint8_t)st;
 }
 
+// ---- stage E as two kernels for batches that cannot fill the GPU with one proof per thread:
+// D (one thread per survivor): G1 sums, identity checks, affine conversion -> the two pairing inputs;
+// E3 (three lanes per survivor, trio.cuh): Miller loop over the pair table, final exponentiation, verdict.
+__global__ void __launch_bounds__(64)
+    k_plonk_stage_d(const PlonkVkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride,
+                    uint8_t* __restrict__ status, PlonkWork* work, int* list, const int* __restrict__ count,
+                    PlonkDbgPtrs dp) {
+  int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= *count) return;
+  int i = list[slot];
+  if (i < 0) return;
+  G1Aff pf[2];
+  int st = plonk_stage_d(pf, work[i], *vk, proofs + stride * (size_t)i, plonk_dbg(dp, i));
+  if (st != BN254V_OK_TRUE) {
+    status[i] = (uint8_t)st;
+    list[slot] = -(i + 1);
+  } else {
+    work[i].pair[0] = pf[0], work[i].pair[1] = pf[1];
+  }
+}
+
+template <int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB)
+    k_plonk_stage_e3(const PlonkVkDev* __restrict__ vk, uint8_t* __restrict__ status, const PlonkWork* work,
+                     const int* __restrict__ list, const int* __restrict__ count, PlonkDbgPtrs dp) {
+  const int cnt = *count;
+  const int per_block = (TPB / 32) * BN_TRIOS_PER_WARP;
+  if ((int)blockIdx.x * per_block >= cnt) return;  // uniform over the block
+  const size_t slot = trio::trio_slot();
+  bool live = trio::trio_lane_valid() && slot < (size_t)cnt;
+  int i = list[live ? slot : 0];
+  if (i < 0) live = false, i = -(i + 1);
+  G1Aff pf[2] = {vk->g1, vk->g1};  // substitute inputs of idle trios: the pairing contains block-wide barriers
+  if (live) pf[0] = work[i].pair[0], pf[1] = work[i].pair[1];
+  trio::S12 f;
+  trio::miller_loop_pairtab0_s(f, pf, vk->g2_pairs);
+  if (live && dp.m) trio::fp12s_to_bytes(dp.m + 384 * (size_t)i, f);
+  trio::fp12s_final_exponentiation(f, f);
+  if (live && dp.gt) trio::fp12s_to_bytes(dp.gt + 384 * (size_t)i, f);
+  const bool one = trio::fp12s_eq(f, trio::fp12s_one());
+  if (live && trio::lane_j() == 0) status[i] = one ? BN254V_OK_TRUE : BN254V_ERR_PAIRING_CHECK_FAILED;
+}
+
 }  // namespace
 
 namespace launch {
@@ -111,6 +155,15 @@ int plonk_verify(cudaStream_t st, const PlonkArgs& a, int sm_count) {
   if (a.stage_ev) cudaEventRecord(a.stage_ev[2], st);
   k_plonk_terms<<<dim3(g64, n_terms), 64, 0, st>>>(a.vk, a.proofs, a.stride, a.work, a.list, a.count, 1);
   if (a.stage_ev) cudaEventRecord(a.stage_ev[3], st);
+  // Three lanes per proof while one proof per thread would leave the SM sub-partitions short of warps (the number
+  // of survivors is only known on the device: the choice goes by the chunk size).
+  if (cm <= (size_t)trio_max_items(sm_count)) {
+    k_plonk_stage_d<<<g64, 64, 0, st>>>(a.vk, a.proofs, a.stride, a.status, a.work, a.list, a.count, dp);
+    const unsigned per_block = (128 / 32) * BN_TRIOS_PER_WARP;
+    k_plonk_stage_e3<128, 3><<<(unsigned)((cm + per_block - 1) / per_block), 128, trio::trio_smem_bytes(128), st>>>(
+        a.vk, a.status, a.work, a.list, a.count, dp);
+    return 6;
+  }
   if (pick_shape(cm, sm_count) == SHAPE_32)
     k_plonk_stage_e<32><<<(unsigned)((cm + 31) / 32), 32, 0, st>>>(a.vk, a.proofs, a.stride, a.status, a.work, a.list,
                                                                    a.count, dp);

@@ -14,6 +14,9 @@ namespace launch {
 // Launch shape of the per-proof pairing kernels for a batch of m items (see k_groth16.cu).
 enum Shape { SHAPE_32 = 6, SHAPE_128 = 1, SHAPE_448 = 3, SHAPE_384 = 10 };
 int pick_shape(size_t m, int sm_count);
+// Largest batch that runs the pairing with three lanes per item (trio.cuh) instead of one item per thread
+// (BN254V_TRIO_MAX overrides; 0 disables the three-lane kernels).
+size_t trio_max_items(int sm_count);
 
 // ---- VK-constant precomputation (once per VK and device)
 int groth16_vk_prepare(cudaStream_t st, Groth16VkDev* dv, int n_bases, G1Aff* table);

@@ -262,6 +262,7 @@ struct PlonkWork {
   G1Jac part[BN_PLONK_MAX_T];      // term results of the current stage
   Fr zeta;                         // Montgomery
   G1Aff lin;                       // linearised polynomial digest
+  G1Aff pair[2];                   // G1 inputs of the final pairing check (stage D -> three-lane stage E)
 };
 HD int plonk_n_terms(const PlonkVkDev& vk, int stage) { return vk.n_qcp + 10; }  // both stages: nQcp + 10
 
@@ -533,49 +534,55 @@ HD int plonk_stage_c(PlonkWork& w, const PlonkVkDev& vk, const uint8_t* pr, cons
   return BN254V_OK_TRUE;
 }
 
+// The G1 side of kzg::fold and kzg::batch_verify_multi_points (plonk/kzg.rs:74-85, 128-178): sums of the term results
+// with the reference's AffineG1 conversions (an identity intermediate panics there) -> the two G1 inputs of the pairing.
+HD int plonk_stage_d(G1Aff* pf, PlonkWork& w, const PlonkVkDev& vk, const uint8_t* pr, const PlonkDebug& dbg) {
+  const int nq = vk.n_qcp, b = 5 + nq;
+  int st = BN254V_OK_TRUE;
+  // folded digest = lin + sum gamma^i D_i (kzg::fold)
+  G1Jac fd = to_jac(w.lin);
+  for (int t = 0; t < b; t++) fd = jac_add(fd, w.part[t]);
+  if (is_identity(fd)) st = BN254V_PANIC_IDENTITY;
+  if (st == BN254V_OK_TRUE && dbg.g1) {
+    G1Aff t;
+    to_affine(t, fd);
+    store_g1(dbg.g1 + 64, t);
+  }
+  G1Aff bh;
+  load_g1_unchecked(bh, pr + 448);
+  G1Jac fq = jac_add_mixed(w.part[b + 0], bh);  // folded quotients = batchedH + rnd zsH
+  if (is_identity(fq)) st = BN254V_PANIC_IDENTITY;
+  G1Jac fdg = jac_add(fd, w.part[b + 1]);       // folded digests = folded + rnd Z
+  if (is_identity(fdg)) st = BN254V_PANIC_IDENTITY;
+  G1Jac fec = w.part[b + 2];                    // vk.g1 * folded evals
+  if (is_identity(fec)) st = BN254V_PANIC_IDENTITY;
+  fec.y = neg(fec.y);
+  fdg = jac_add(fdg, fec);
+  if (is_identity(fdg)) st = BN254V_PANIC_IDENTITY;
+  G1Jac fpq = jac_add(w.part[b + 3], w.part[b + 4]);  // zeta batchedH + rnd omega zeta zsH
+  if (is_identity(fpq)) st = BN254V_PANIC_IDENTITY;
+  fdg = jac_add(fdg, fpq);
+  if (is_identity(fdg)) st = BN254V_PANIC_IDENTITY;
+  fq.y = neg(fq.y);
+  if (st == BN254V_OK_TRUE) {
+    to_affine2(pf[0], fdg, pf[1], fq);  // both checked non-identity above; one shared inversion
+    if (dbg.g1) {
+      store_g1(dbg.g1 + 128, pf[0]);
+      store_g1(dbg.g1 + 192, pf[1]);
+    }
+  }
+  return st;
+}
+
 // `live == false`: a spare thread, or a proof that stage C already ended -- the pairing below contains block-wide
 // phase barriers, so the thread still runs it (on VK points) and its result is discarded.  For the same reason the
 // identity panics of the reference's AffineG1 conversions are recorded and the pairing runs on substitute points.
 HD int plonk_stage_e(PlonkWork& w, const PlonkVkDev& vk, const uint8_t* pr, const PlonkDebug& dbg, bool live = true) {
-  const int nq = vk.n_qcp, b = 5 + nq;
   int st = live ? BN254V_OK_TRUE : BN254V_STATUS_UNSET;
   G1Aff pf[2] = {vk.g1, vk.g1};
-  if (live) {
-    // folded digest = lin + sum gamma^i D_i (kzg::fold)
-    G1Jac fd = to_jac(w.lin);
-    for (int t = 0; t < b; t++) fd = jac_add(fd, w.part[t]);
-    if (is_identity(fd)) st = BN254V_PANIC_IDENTITY;
-    if (st == BN254V_OK_TRUE && dbg.g1) {
-      G1Aff t;
-      to_affine(t, fd);
-      store_g1(dbg.g1 + 64, t);
-    }
-    // ---- kzg::batch_verify_multi_points (plonk/kzg.rs:128-190), with the reference's AffineG1 conversions (identity panics)
-    G1Aff bh;
-    load_g1_unchecked(bh, pr + 448);
-    G1Jac fq = jac_add_mixed(w.part[b + 0], bh);  // folded quotients = batchedH + rnd zsH
-    if (is_identity(fq)) st = BN254V_PANIC_IDENTITY;
-    G1Jac fdg = jac_add(fd, w.part[b + 1]);       // folded digests = folded + rnd Z
-    if (is_identity(fdg)) st = BN254V_PANIC_IDENTITY;
-    G1Jac fec = w.part[b + 2];                    // vk.g1 * folded evals
-    if (is_identity(fec)) st = BN254V_PANIC_IDENTITY;
-    fec.y = neg(fec.y);
-    fdg = jac_add(fdg, fec);
-    if (is_identity(fdg)) st = BN254V_PANIC_IDENTITY;
-    G1Jac fpq = jac_add(w.part[b + 3], w.part[b + 4]);  // zeta batchedH + rnd omega zeta zsH
-    if (is_identity(fpq)) st = BN254V_PANIC_IDENTITY;
-    fdg = jac_add(fdg, fpq);
-    if (is_identity(fdg)) st = BN254V_PANIC_IDENTITY;
-    fq.y = neg(fq.y);
-    if (st == BN254V_OK_TRUE) {
-      to_affine2(pf[0], fdg, pf[1], fq);  // both checked non-identity above; one shared inversion
-      if (dbg.g1) {
-        store_g1(dbg.g1 + 128, pf[0]);
-        store_g1(dbg.g1 + 192, pf[1]);
-      }
-    }
-  }
+  if (live) st = plonk_stage_d(pf, w, vk, pr, dbg);
   const bool ok = st == BN254V_OK_TRUE;
+  if (!ok) pf[0] = pf[1] = vk.g1;
   Fp12 f;
   miller_loop_pairtab<0>(f, nullptr, nullptr, pf, vk.g2_pairs);
   if (ok && dbg.miller) fp12_to_bytes(dbg.miller, f);

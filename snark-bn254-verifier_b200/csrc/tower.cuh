@@ -55,7 +55,7 @@ HD bool eq(const Fp2& a, const Fp2& b) { return fe_eq(a.c0, b.c0) && fe_eq(a.c1,
 // the 408 of three Montgomery multiplications).  Out of line, operands by value (registers): one copy in the binary.
 //   c0 = a0 b0 - a1 b1           (+ p 2^256 when negative: still < p 2^256 and congruent)
 //   c1 = (a0 + a1)(b0 + b1) - a0 b0 - a1 b1      (sums unreduced, < 2p; the difference is a0 b1 + a1 b0 >= 0)
-HDN Fp2 mul(Fp2 a, Fp2 b) {
+HD Fp2 mul_inl(const Fp2& a, const Fp2& b) {
   uint32_t T0[16], T1[16], S[16];
   fe_mul_wide(T0, a.c0, b.c0);
   fe_mul_wide(T1, a.c1, b.c1);
@@ -68,6 +68,7 @@ HDN Fp2 mul(Fp2 a, Fp2 b) {
   r.c0 = fe_redc_wide<FpCfg>(T0);
   return r;
 }
+HDN Fp2 mul(Fp2 a, Fp2 b) { return mul_inl(a, b); }
 // (a0+a1)(a0-a1), 2 a0 a1
 HDN Fp2 sqr(Fp2 a) {
   Fp c1 = fe_mul(fe_add_nr(a.c0, a.c0), a.c1);  // 2 a0 a1 (first operand < 2p)

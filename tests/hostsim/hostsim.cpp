@@ -248,3 +248,70 @@ void hs_sha256(const uint8_t* data, uint32_t len, uint8_t* out) {
   sha256_final(s, out);
 }
 }
+
+// ---- three lanes per proof (csrc/trio.cuh): the host build runs the three lanes in lock-step ---------------------
+#include "../../snark-bn254-verifier_b200/csrc/trio.cuh"
+
+extern "C" {
+// a, b: Fq12 values as 96 Montgomery words each (c0.c0 c0.c1 c0.c2 c1.c0 c1.c1 c1.c2).  Runs every sliced Fq12
+// operation next to the sequential one; returns a bit mask of the operations whose results differ (0 = all equal):
+// 1 mul, 2 sqr, 4 cyclotomic_sqr(a), 8 inv, 16/32/64 frobenius 1/2/3, 128 aliased mul/sqr, 256 conj.
+int hs_trio_fp12_ops(const uint32_t* aw, const uint32_t* bw) {
+  Fp12 a, b, want, got;
+  memcpy(&a, aw, 384), memcpy(&b, bw, 384);
+  const trio::S12 sa = trio::fp12s_load(a), sb = trio::fp12s_load(b);
+  trio::S12 sr;
+  int bad = 0;
+  mul(want, a, b), trio::fp12s_mul(sr, sa, sb), trio::fp12s_store(got, sr);
+  if (memcmp(&want, &got, 384)) bad |= 1;
+  sqr(want, a), trio::fp12s_sqr(sr, sa), trio::fp12s_store(got, sr);
+  if (memcmp(&want, &got, 384)) bad |= 2;
+  cyclotomic_sqr(want, a), trio::fp12s_cyclotomic_sqr(sr, sa), trio::fp12s_store(got, sr);
+  if (memcmp(&want, &got, 384)) bad |= 4;
+  inv(want, a), trio::fp12s_inv(sr, sa), trio::fp12s_store(got, sr);
+  if (memcmp(&want, &got, 384)) bad |= 8;
+  frobenius<1>(want, a), trio::fp12s_frobenius<1>(sr, sa), trio::fp12s_store(got, sr);
+  if (memcmp(&want, &got, 384)) bad |= 16;
+  frobenius<2>(want, a), trio::fp12s_frobenius<2>(sr, sa), trio::fp12s_store(got, sr);
+  if (memcmp(&want, &got, 384)) bad |= 32;
+  frobenius<3>(want, a), trio::fp12s_frobenius<3>(sr, sa), trio::fp12s_store(got, sr);
+  if (memcmp(&want, &got, 384)) bad |= 64;
+  {  // destination aliases an operand
+    trio::S12 t = sa;
+    trio::fp12s_mul(t, t, sb), trio::fp12s_sqr(t, t), trio::fp12s_cyclotomic_sqr(t, t), trio::fp12s_store(got, t);
+    mul(want, a, b), sqr(want, want), cyclotomic_sqr(want, want);
+    if (memcmp(&want, &got, 384)) bad |= 128;
+  }
+  conj(want, a), trio::fp12s_store(got, trio::fp12s_conj(sa));
+  if (memcmp(&want, &got, 384)) bad |= 256;
+  return bad;
+}
+// final exponentiation of a canonical Fq12 value, sliced: writes the canonical result
+void hs_trio_final_exp(const uint8_t* f_be, uint8_t* out_be) {
+  Fp12 f;
+  Fp2* cs[6] = {&f.c0.c0, &f.c0.c1, &f.c0.c2, &f.c1.c0, &f.c1.c1, &f.c1.c2};
+  for (int i = 0; i < 6; i++) {
+    fp_load_be(cs[i]->c0, f_be + 64 * i);
+    fp_load_be(cs[i]->c1, f_be + 64 * i + 32);
+  }
+  trio::S12 r;
+  trio::fp12s_final_exponentiation(r, trio::fp12s_load(f));
+  trio::fp12s_store(f, r);
+  fp12_to_bytes(out_be, f);
+}
+// Miller value of the two-pair KZG check of a PlonK VK for G1 points pf (2 x 64 bytes), sliced and sequential:
+// returns 0 when equal; writes the sliced canonical bytes
+int hs_trio_plonk_miller(void* vkp, const uint8_t* pf_be, uint8_t* out_be) {
+  const PlonkVkDev& vk = *(PlonkVkDev*)vkp;
+  G1Aff pf[2];
+  load_g1_unchecked(pf[0], pf_be);
+  load_g1_unchecked(pf[1], pf_be + 64);
+  Fp12 want, got;
+  miller_loop_pairtab<0>(want, nullptr, nullptr, pf, vk.g2_pairs);
+  trio::S12 f;
+  trio::miller_loop_pairtab0_s(f, pf, vk.g2_pairs);
+  trio::fp12s_store(got, f);
+  fp12_to_bytes(out_be, got);
+  return memcmp(&want, &got, 384) ? 1 : 0;
+}
+}

@@ -367,3 +367,46 @@ def test_pairing_product_skips_identity_pairs(hs):
         one = hs.hs_pairing_product(3, bytes(a), bytes(b), ml, gt)
         assert ml.raw == bo.fp12_to_bytes(m) and gt.raw == bo.fp12_to_bytes(want_gt), (zero_g1, zero_g2)
         assert bool(one) == (want_gt == bo.FP12_ONE)
+
+
+# ------------------------------------------------------------------------------------------------ three lanes per proof
+def _fp12_words(rng):
+    """a random Fq12 element as 96 Montgomery words (12 coefficients, little-endian limbs)"""
+    out = b""
+    for _ in range(12):
+        v = (int.from_bytes(rng.bytes(40), "big") % bo.P) * (1 << 256) % bo.P
+        out += v.to_bytes(32, "little")
+    return out
+
+
+def test_trio_fp12_operations_equal_the_sequential_ones(hs):
+    """csrc/trio.cuh (three lanes per proof, sliced at Fq2 granularity), run in lock-step on the host: every Fq12
+    operation gives the same limbs as tower_body.inc, also with edge operands (zero / one coefficients)."""
+    rng = np.random.default_rng(7)
+    one = (1 << 256) % bo.P
+    cases = [(_fp12_words(rng), _fp12_words(rng)) for _ in range(12)]
+    sparse = bytearray(_fp12_words(rng))
+    sparse[64:128] = bytes(64)
+    sparse[320:384] = bytes(64)
+    cases.append((bytes(sparse), _fp12_words(rng)))
+    unit = one.to_bytes(32, "little") + bytes(352)
+    cases.append((_fp12_words(rng), unit))
+    pm1 = ((bo.P - 1) * (1 << 256) % bo.P).to_bytes(32, "little")
+    cases.append((pm1 * 12, pm1 * 12))
+    for a, b in cases:
+        assert hs.hs_trio_fp12_ops(a, b) == 0
+
+
+def test_trio_final_exponentiation_and_plonk_miller(hs):
+    """The sliced final exponentiation on the golden Miller values, and the sliced two-pair Miller loop of the PlonK
+    KZG check (pair table) on the golden pairing inputs: canonical bytes as committed."""
+    out = ctypes.create_string_buffer(384)
+    for c in load_json("pairing_golden.json"):
+        hs.hs_trio_final_exp(bytes.fromhex(c["miller"]), out)
+        assert out.raw.hex() == c["gt"]
+    vk = _hs_plonk(hs)
+    hs.hs_trio_plonk_miller.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p]
+    for prog, g in load_json("plonk_golden.json").items():
+        pf = pt_bytes(g["pair_g1"][0]) + pt_bytes(g["pair_g1"][1])
+        assert hs.hs_trio_plonk_miller(vk, pf, out) == 0
+        assert out.raw.hex() == g["miller"]

@@ -1,11 +1,14 @@
-import sys, time
-sys.path.insert(0, '/root/repo')
-import __graft_entry__ as ge, workloads
+"""One PlonK batch through the C ABI (profiling target): python tools/probe/plonk_only.py [log2 batch] [repeats]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge
+import workloads
 pkg = ge.load_package(); pkg.init([0])
-n = 1 << 14
-proofs, inputs, rnd, expected = workloads.plonk_workload(n, seed=3)
-vk = workloads.plonk_vk_bytes()
-for it in range(3):
-    t0 = time.perf_counter(); st = pkg.PlonkVerifier.verify_batch(proofs, vk, inputs, rnd=rnd); dt = time.perf_counter() - t0
-    assert (st == expected).all()
-print("plonk 2^14 ms", dt * 1e3)
+n = 1 << (int(sys.argv[1]) if len(sys.argv) > 1 else 14)
+p, i, r, e = workloads.plonk_workload(n, seed=3)
+b = pkg.PlonkDeviceBatch(workloads.plonk_vk_bytes(), p, i, r)
+for _ in range(int(sys.argv[2]) if len(sys.argv) > 2 else 3):
+    st, ms = b.verify()
+    assert (st == e).all()
+print("ok", ms, pkg.last_stage_ms())
