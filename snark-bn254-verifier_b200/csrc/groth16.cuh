@@ -99,10 +99,10 @@ struct Groth16Debug {
 // block must reach them the same number of times.  A proof that fails before the Miller loop is therefore NOT ended
 // early: its status is recorded and the thread runs the loop on substitute VK points (always valid, order r), whose
 // result is discarded.  `live == false` (a spare thread of the last block) does the same and writes nothing.
-HD int groth16_miller_one(Fp12& f, const Groth16VkDev& vk, const uint8_t* proof, uint32_t proof_len,
-                          const uint8_t* inputs_be, int n_inputs, const Groth16Debug& dbg, bool live = true) {
-  G1Aff A, C, L;
-  G2Aff B;
+// Decode, validate and prepare_inputs: everything of a proof that precedes the Miller loop.  On BN254V_OK_TRUE the
+// points A, B (on the curve; its G2 membership is read off the Miller loop's end point), C and L are set.
+HD int groth16_parse_one(G1Aff& A, G2Aff& B, G1Aff& C, G1Aff& L, const Groth16VkDev& vk, const uint8_t* proof,
+                         uint32_t proof_len, const uint8_t* inputs_be, int n_inputs, bool live = true) {
   int st = BN254V_OK_TRUE;
   if (!live) st = BN254V_STATUS_UNSET;
   else if (proof_len < 256) st = BN254V_PANIC_SHORT_BUFFER;
@@ -110,7 +110,7 @@ HD int groth16_miller_one(Fp12& f, const Groth16VkDev& vk, const uint8_t* proof,
   if (st == BN254V_OK_TRUE) {
     st = load_g2_on_curve(B, proof + 64);
     if (st == BN254V_OK_TRUE) {
-      // B's subgroup test (the last check of AffineG2::new) is read off the end point of the Miller loop below.  The
+      // B's subgroup test (the last check of AffineG2::new) is read off the end point of the Miller loop.  The
       // reference parses B before C and before the public inputs, so on a later failure B's verdict still comes first
       // (rare path, separate scalar multiplication, no barriers).
       st = load_g1_checked(C, proof + 192);
@@ -118,6 +118,13 @@ HD int groth16_miller_one(Fp12& f, const Groth16VkDev& vk, const uint8_t* proof,
       if (st != BN254V_OK_TRUE && !g2_in_subgroup<false>(B)) st = BN254V_PANIC_NOT_IN_SUBGROUP;
     }
   }
+  return st;
+}
+HD int groth16_miller_one(Fp12& f, const Groth16VkDev& vk, const uint8_t* proof, uint32_t proof_len,
+                          const uint8_t* inputs_be, int n_inputs, const Groth16Debug& dbg, bool live = true) {
+  G1Aff A, C, L;
+  G2Aff B;
+  const int st = groth16_parse_one(A, B, C, L, vk, proof, proof_len, inputs_be, n_inputs, live);
   const bool ok = st == BN254V_OK_TRUE;
   if (!ok) A = vk.alpha, B = vk.beta, L = vk.ic[0], C = vk.ic[0];  // substitute inputs; the result is discarded
 

@@ -75,6 +75,75 @@ __global__ void __launch_bounds__(TPB, 1)
   if (decide) status[i] = (uint8_t)st;
 }
 
+// ---- three lanes per proof (trio.cuh) for batches that cannot fill the GPU with one proof per thread ------------
+// prepare (one thread per proof): decode, validate, prepare_inputs -> L, parked in the first 64 bytes of fbuf[i];
+// miller3 / finish3 (three lanes per proof): the pairing.  Same statuses, same canonical values.
+__global__ void __launch_bounds__(64)
+    k_groth16_prepare(const Groth16VkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride,
+                      const uint32_t* __restrict__ proof_len, const uint8_t* __restrict__ inputs, int n_inputs, size_t n,
+                      uint8_t* __restrict__ status, Fp12* __restrict__ fbuf, uint8_t* dbg_l) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;  // (no barriers in this kernel)
+  uint32_t len = proof_len ? proof_len[i] : (uint32_t)stride;
+  if (len > stride) len = (uint32_t)stride;
+  G1Aff A, C, L;
+  G2Aff B;
+  int st = groth16_parse_one(A, B, C, L, *vk, proofs + stride * i, len, inputs + (size_t)32 * n_inputs * i, n_inputs);
+  if (st == BN254V_OK_TRUE) {
+    *(G1Aff*)&fbuf[i] = L;
+    status[i] = BN254V_STATUS_UNSET;
+  } else {
+    status[i] = (uint8_t)st;
+  }
+}
+
+template <int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB)
+    k_groth16_miller3(const Groth16VkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride, size_t n,
+                      uint8_t* __restrict__ status, Fp12* __restrict__ fbuf, uint8_t* dbg_l, uint8_t* dbg_m) {
+  size_t i = trio::trio_slot();
+  bool live = trio::trio_lane_valid() && i < n;
+  if (!live) i = 0;
+  if (status[i] != BN254V_STATUS_UNSET) live = false;  // failed in k_groth16_prepare: keeps its status
+  G1Aff A = vk->alpha, pf[2] = {vk->ic[0], vk->ic[0]};  // substitutes of idle trios (block-wide barriers inside)
+  G2Aff B = vk->beta;
+  if (live) {
+    const uint8_t* pr = proofs + stride * i;
+    load_g1_unchecked(A, pr);  // validated by k_groth16_prepare
+    load_g2_unchecked(B, pr + 64);
+    load_g1_unchecked(pf[1], pr + 192);
+    pf[0] = *(const G1Aff*)&fbuf[i];
+  }
+  trio::S12 f;
+  bool in_g2;
+  trio::miller_loop_pairtab1_s(f, A, B, pf, vk->gd_pairs, &in_g2);
+  if (!live) return;
+  if (!in_g2) {
+    if (trio::lane_j() == 0) status[i] = BN254V_PANIC_NOT_IN_SUBGROUP;
+    return;
+  }
+  if (dbg_l && trio::lane_j() == 0) store_g1(dbg_l + 64 * i, pf[0]);
+  if (dbg_m) trio::fp12s_to_bytes(dbg_m + 384 * i, f);
+  trio::fp12s_store(fbuf[i], f);
+}
+
+template <int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB)
+    k_groth16_finish3(const Groth16VkDev* __restrict__ vk, size_t n, uint8_t* __restrict__ status,
+                      const Fp12* __restrict__ fbuf, uint8_t* dbg_gt) {
+  size_t i = trio::trio_slot();
+  bool live = trio::trio_lane_valid() && i < n;
+  if (!live) i = 0;
+  if (status[i] != BN254V_STATUS_UNSET) live = false;
+  const trio::S12 target = trio::fp12s_load(vk->target);
+  trio::S12 f = live ? trio::fp12s_load(fbuf[i]) : target;
+  trio::fp12s_final_exponentiation(f, f);
+  if (!live) return;
+  if (dbg_gt) trio::fp12s_to_bytes(dbg_gt + 384 * i, f);
+  const bool ok = trio::fp12s_eq(f, target);
+  if (trio::lane_j() == 0) status[i] = ok ? BN254V_OK_TRUE : BN254V_OK_FALSE;
+}
+
 }  // namespace
 
 namespace launch {
@@ -112,6 +181,19 @@ int groth16_vk_prepare(cudaStream_t st, Groth16VkDev* dv, int n_bases, G1Aff* ta
 int groth16_verify(cudaStream_t st, const Groth16Args& a, int sm_count, bool* two_launch) {
   const int shape = pick_shape(a.m, sm_count);
   const size_t m = a.m;
+  if (a.fbuf && m <= trio_max_items(sm_count)) {  // small batch: three lanes per proof
+    constexpr int TPB = 128;
+    const unsigned per_block = (TPB / 32) * BN_TRIOS_PER_WARP;
+    const unsigned grid = (unsigned)((m + per_block - 1) / per_block);
+    if (two_launch) *two_launch = true;
+    k_groth16_prepare<<<(unsigned)((m + 63) / 64), 64, 0, st>>>(a.vk, a.proofs, a.stride, a.lens, a.inputs, a.n_inputs, m,
+                                                               a.status, a.fbuf, a.dbg_l);
+    k_groth16_miller3<TPB, 3><<<grid, TPB, trio::trio_smem_bytes(TPB), st>>>(a.vk, a.proofs, a.stride, m, a.status, a.fbuf,
+                                                                            a.dbg_l, a.dbg_m);
+    if (a.mid) cudaEventRecord(a.mid, st);
+    k_groth16_finish3<TPB, 3><<<grid, TPB, trio::trio_smem_bytes(TPB), st>>>(a.vk, m, a.status, a.fbuf, a.dbg_gt);
+    return 3;
+  }
   // Big batches: two launches (Miller loop | final exponentiation), each with about half the code and stack of the fused
   // kernel -- measured 2 % faster at 2^16 and 2^18.
   if (a.fbuf && (shape == SHAPE_448 || shape == SHAPE_384)) {

@@ -119,7 +119,12 @@ TRIO_FN V2 v_xi(const V2& a) { return mul_xi(a); }
 TRIO_FN V2 v_scale(const V2& a, const V1& k) { return scale(a, k); }
 TRIO_FN V2 v_scale2_add(const V2& a, const V1& j, const V2& b, const V1& k) { return scale2_add(a, j, b, k); }
 TRIO_FN V2 v_inv(const V2& a) { return inv(a); }
+TRIO_FN V2 v_halve(const V2& a) { return fp2_halve(a); }
+TRIO_FN V2 v_embed(const V1& k) { return V2{k, fe_zero<FpCfg>()}; }
+TRIO_FN bool v_is_zero_lane(const V2& a) { return is_zero(a); }
 TRIO_FN bool v_eq(const V2& a, const V2& b) { return tri_all(eq(a, b)); }
+// lane 0: a == b, lane 1: a == b, lane 2: a != 0 -- all three must hold (end-point test of the G2 chain)
+TRIO_FN bool v_eq_eq_nz(const V2& a, const V2& b) { return tri_all(lane_j() == 2 ? !is_zero(a) : eq(a, b)); }
 TRIO_FN V2 v_zero() { return fp2_zero(); }
 TRIO_FN V2 v_const(const Fp2& x0, const Fp2& x1, const Fp2& x2) { return tri_sel(x0, x1, x2); }
 TRIO_FN V1 v_const(const Fp& x0, const Fp& x1, const Fp& x2) { return tri_sel(x0, x1, x2); }
@@ -183,7 +188,10 @@ inline V2 v_scale2_add(const V2& a, const V1& j, const V2& b, const V1& k) {
   return r;
 }
 inline V2 v_inv(const V2& a) { V2 r; TRIO_EACH(r.l[_j] = inv(a.l[_j])) return r; }
+inline V2 v_halve(const V2& a) { V2 r; TRIO_EACH(r.l[_j] = fp2_halve(a.l[_j])) return r; }
+inline V2 v_embed(const V1& k) { V2 r; TRIO_EACH(r.l[_j] = (Fp2{k.l[_j], fe_zero<FpCfg>()})) return r; }
 inline bool v_eq(const V2& a, const V2& b) { return eq(a.l[0], b.l[0]) && eq(a.l[1], b.l[1]) && eq(a.l[2], b.l[2]); }
+inline bool v_eq_eq_nz(const V2& a, const V2& b) { return eq(a.l[0], b.l[0]) && eq(a.l[1], b.l[1]) && !is_zero(a.l[2]); }
 inline V2 v_zero() { return V2{{fp2_zero(), fp2_zero(), fp2_zero()}}; }
 inline V2 v_const(const Fp2& x0, const Fp2& x1, const Fp2& x2) { return V2{{x0, x1, x2}}; }
 inline V1 v_const(const Fp& x0, const Fp& x1, const Fp& x2) { return V1{{x0, x1, x2}}; }
@@ -422,6 +430,201 @@ TRIO_FN_NOINLINE void miller_loop_pairtab0_s(S12& f, const G1Aff* pf, const Line
   fp12s_mul(f, f, M);
   eval_line_pair_s(M, ptab[idx + 1], ps);
   fp12s_mul(f, f, M);
+}
+
+
+// ------------------------------------------------------------------------------------------ G2 steps, sliced
+// The running point R = (X, Y, Z) of a variable G2 point lives one coordinate per lane (lane 0 X, lane 1 Y, lane 2 Z).
+// A line (x0 + x2 v^2 + x4 v w, pairing_body.inc Line3) is the sparse S12 {c0: (x0, 0, x2), c1: (0, x4, 0)}, i.e. lane 0
+// holds (x0, 0), lane 1 (0, x4), lane 2 (x2, 0).  The step formulas are those of pairing_body.inc (doubling_step_at,
+// addition_step_at); every round below is one multiplication per lane on per-lane operands.
+TRIO_FN S12 line_pack(const V2& at0, const V2& at1, const V2& at2) {  // x0 held by lane 0, x4 by lane 1, x2 by lane 2
+  const V2 z = v_zero();
+  return S12{tri_sel(at0, z, at2), tri_sel(z, at1, z)};
+}
+TRIO_FN S12 line_one_s() { return fp12s_one(); }
+
+// R <- 2R; line = tangent at R evaluated at P = (px, py)
+TRIO_FN_NOINLINE void doubling_step_s(S12& line, V2& r, const V1& px, const V1& py) {
+  const V2 s1 = v_sqr(r);                                   // (j = X^2, b = Y^2, c = Z^2)
+  tri_put(r);
+  const V2 o = tri_fetch(1, 2, 2);                          // lane 0: Y, lane 1: Z
+  const V2 yz = v_add(r, o);                                // lane 1: Y + Z
+  const V2 s3 = v_add(v_dbl(s1), s1);                       // lane 0: vv = 3 j, lane 2: 3 c
+  const V2 m2 = v_mul(tri_sel(r, yz, v_bcast(fp2_b2())), tri_sel(o, yz, s3));  // (X Y, (Y + Z)^2, e = b' 3 c)
+  tri_put(s1);
+  const V2 sc = tri_fetch(1, 2, 1);                         // lane 0: b, lane 1: c, lane 2: b
+  const V2 h = v_sub(v_sub(m2, s1), sc);                    // lane 1: h = (Y + Z)^2 - b - c
+  tri_put(m2);
+  const V2 e = tri_fetch(2, 2, 2);
+  const V2 f = v_add(v_dbl(e), e);                          // 3 e
+  const V2 bb = tri_sel(sc, s1, sc);                        // b on every lane
+  const V2 g = v_halve(v_add(bb, f));
+  const V2 m3 = v_mul(tri_sel(v_halve(m2), g, e), tri_sel(v_sub(bb, f), g, e));  // (X' = a (b - f), g^2, e^2)
+  tri_put(m3);
+  const V2 e2 = tri_fetch(2, 2, 2);
+  const V2 y3 = v_sub(m3, v_add(v_dbl(e2), e2));            // lane 1: Y' = g^2 - 3 e^2
+  tri_put(h);
+  const V2 hh = tri_fetch(1, 1, 1);
+  // (x2 = vv px on lane 0, x4 = -h py on lane 1, Z' = b h on lane 2)
+  const V2 m4 = v_mul(tri_sel(s3, v_neg(h), bb), tri_sel(v_embed(px), v_embed(py), hh));
+  const V2 x0 = v_xi(v_sub(e, bb));                          // every lane has e and b
+  r = tri_sel(m3, y3, m4);
+  tri_put(m4);
+  line = line_pack(x0, m4, tri_fetch(0, 0, 0));
+}
+
+// R <- R + Q for the affine point Q = (qx, qy) (the same values on the three lanes); line = chord evaluated at P
+TRIO_FN_NOINLINE void addition_step_s(S12& line, V2& r, const V2& qx, const V2& qy, const V1& px, const V1& py) {
+  tri_put(r);
+  const V2 z = tri_fetch(2, 2, 2), x = tri_fetch(0, 0, 0);
+  const V2 de = v_sub(r, v_mul(z, tri_sel(qx, qy, qx)));    // lane 0: d = X - Z qx, lane 1: e = Y - Z qy
+  tri_put(de);
+  const V2 d = tri_fetch(0, 0, 0), e = tri_fetch(1, 1, 1);
+  const V2 m2a = v_mul(tri_sel(d, e, e), tri_sel(d, e, qx));                       // (f = d^2, e^2, e qx)
+  const V2 m2b = v_mul(tri_sel(d, v_neg(e), d), tri_sel(v_embed(py), v_embed(px), qy));  // (x4 = d py, x2 = -e px, d qy)
+  const V2 x0 = v_xi(v_sub(m2a, m2b));                       // lane 2: xi (e qx - d qy)
+  tri_put(tri_sel(m2b, m2b, x0));
+  line = line_pack(tri_fetch(2, 2, 2), tri_fetch(0, 0, 0), tri_fetch(1, 1, 1));
+  tri_put(m2a);
+  const V2 ff = tri_fetch(0, 0, 0);
+  const V2 m3 = v_mul(tri_sel(d, z, x), tri_sel(ff, m2a, ff));  // (h = d f, Z e^2, i = X f)
+  tri_put(m3);
+  const V2 hh = tri_fetch(0, 0, 0), ze2 = tri_fetch(1, 1, 1), ii = tri_fetch(2, 2, 2);
+  const V2 jj = v_sub(v_add(ze2, hh), v_dbl(ii));            // j = Z e^2 + h - 2 i
+  const V2 m4a = v_mul(tri_sel(d, e, z), tri_sel(jj, v_sub(ii, jj), hh));  // (X' = d j, e (i - j), Z' = Z h)
+  const V2 m4b = v_mul(hh, r);                               // lane 1: h Y
+  r = tri_sel(m4a, v_sub(m4a, m4b), m4a);
+}
+
+// M = l1 l2 for two sparse lines (pairing_body.inc mul_lines): 6 Fq2 multiplications in two rounds
+TRIO_FN_NOINLINE void mul_lines_s(S12& M, const S12& l1, const S12& l2) {
+  const V2 a = tri_sel(l1.c0, l1.c1, l1.c0), b = tri_sel(l2.c0, l2.c1, l2.c0);  // (x0, x4, x2), (y0, y4, y2)
+  const V2 p = v_mul(a, b);                                  // (p00, p44, p22)
+  tri_put(a);
+  const V2 sa = v_add(a, tri_fetch(2, 0, 1));                // (x0 + x2, x4 + x0, x2 + x4)
+  tri_put(b);
+  const V2 sb = v_add(b, tri_fetch(2, 0, 1));
+  const V2 cr = v_mul(sa, sb);
+  tri_put(p);
+  const V2 pa = tri_fetch(1, 2, 0), pb = tri_fetch(2, 0, 1);  // (p44, p22, p00), (p22, p00, p44)
+  const V2 u = v_sub(v_sub(cr, p), pb);                      // lane 0: m2, lane 1: n1, lane 2: n0 / xi
+  const V2 xw = v_xi(tri_sel(pa, pa, u));                    // lane 0: xi p44, lane 1: m1 = xi p22, lane 2: n0
+  tri_put(tri_sel(u, u, xw));
+  const V2 g = tri_fetch(2, 2, 0);                           // lane 0: n0, lane 2: m2
+  M.c0 = tri_sel(v_add(p, xw), xw, g);
+  M.c1 = tri_sel(g, u, v_zero());
+}
+
+// psi(Q) for an affine G2 point given on all lanes (curve_body.inc g2_psi)
+TRIO_FN void g2_psi_s(V2& ox, V2& oy, const V2& qx, const V2& qy) {
+  ox = v_mul(v_conj(qx), v_bcast(frob_coeff<1>(2)));
+  oy = v_mul(v_conj(qy), v_bcast(frob_coeff<1>(3)));
+}
+// R == -psi^3(Q) with Z != 0 (pairing_body.inc ate_endpoint_in_g2); (q2x, q2y) = -psi^2(Q)
+TRIO_FN_NOINLINE bool ate_endpoint_in_g2_s(const V2& r, const V2& q2x, const V2& q2y) {
+  V2 tx, ty;
+  g2_psi_s(tx, ty, q2x, q2y);
+  tri_put(r);
+  const V2 z = tri_fetch(2, 2, 2);
+  const V2 m = v_mul(tri_sel(tx, ty, v_bcast(fp2_one())), z);  // (tx Z, ty Z, Z)
+  return v_eq_eq_nz(tri_sel(r, r, m), m);
+}
+
+// Shared-accumulator Miller loop: one variable pair (A, B) and the two VK-constant pairs behind the pair table
+// (pairing_body.inc miller_loop_pairtab<1>: same order of operations, same value).  in_g2: B (on the curve) lies in G2.
+TRIO_FN_NOINLINE void miller_loop_pairtab1_s(S12& f, const G1Aff& pa, const G2Aff& qb, const G1Aff* pf,
+                                             const LinePairKF* ptab, bool* in_g2) {
+  const PairScalarsS ps = pair_scalars_s(pf[0], pf[1]);
+  const V1 px = v_bcast(pa.x), py = v_bcast(pa.y);
+  const V2 qx = v_bcast(qb.x), qy = v_bcast(qb.y), nqy = v_neg(qy);
+  V2 r = v_const(qb.x, qb.y, fp2_one());
+  S12 M, l1, l2;
+  int idx = 0;
+  for (int k = 0; k < 64; k++) {
+    if ((k & (BN_SYNC_PERIOD - 1)) == 0) BN_PHASE_SYNC();
+    eval_line_pair_s(M, ptab[idx], ps);
+    if (k > 0) {
+      fp12s_sqr(f, f);
+      fp12s_mul(f, f, M);
+    } else {
+      f = M;
+    }
+    idx++;
+    doubling_step_s(l1, r, px, py);
+    const int d = K::ate_digit(k);
+    if (d != 0) {
+      eval_line_pair_s(M, ptab[idx], ps);
+      fp12s_mul(f, f, M);
+      idx++;
+      addition_step_s(l2, r, qx, d == 1 ? qy : nqy, px, py);
+      mul_lines_s(M, l1, l2);
+      fp12s_mul(f, f, M);
+    } else {
+      fp12s_mul(f, f, l1);
+    }
+  }
+  BN_PHASE_SYNC();
+  eval_line_pair_s(M, ptab[idx], ps);
+  fp12s_mul(f, f, M);
+  eval_line_pair_s(M, ptab[idx + 1], ps);
+  fp12s_mul(f, f, M);
+  V2 q1x, q1y, q2x, q2y;
+  g2_psi_s(q1x, q1y, qx, qy);
+  g2_psi_s(q2x, q2y, q1x, q1y);
+  q2y = v_neg(q2y);
+  addition_step_s(l1, r, q1x, q1y, px, py);
+  addition_step_s(l2, r, q2x, q2y, px, py);
+  if (in_g2) *in_g2 = ate_endpoint_in_g2_s(r, q2x, q2y);
+  mul_lines_s(M, l1, l2);
+  fp12s_mul(f, f, M);
+}
+
+// Shared-accumulator Miller loop over NV variable pairs (pairing_body.inc miller_loop<NV, 0>); skip: pairs with an
+// identity member contribute the line 1.
+template <int NV>
+TRIO_FN_NOINLINE void miller_loop_var_s(S12& f, const G1Aff* pv, const G2Aff* qv, uint32_t skip) {
+  V2 r[NV];
+  S12 ls[2 * NV], M;
+  for (int v = 0; v < NV; v++) r[v] = v_const(qv[v].x, qv[v].y, fp2_one());
+  f = fp12s_one();
+  for (int k = 0; k < 64; k++) {
+    if ((k & (BN_SYNC_PERIOD - 1)) == 0) BN_PHASE_SYNC();
+    if (k > 0) fp12s_sqr(f, f);
+    for (int v = 0; v < NV; v++) {
+      doubling_step_s(ls[v], r[v], v_bcast(pv[v].x), v_bcast(pv[v].y));
+      if ((skip >> v) & 1) ls[v] = line_one_s();
+    }
+    const int d = K::ate_digit(k);
+    int nl = NV;
+    if (d != 0) {
+      for (int v = 0; v < NV; v++) {
+        const V2 qy = v_bcast(qv[v].y);
+        addition_step_s(ls[NV + v], r[v], v_bcast(qv[v].x), d == 1 ? qy : v_neg(qy), v_bcast(pv[v].x), v_bcast(pv[v].y));
+        if ((skip >> v) & 1) ls[NV + v] = line_one_s();
+      }
+      nl = 2 * NV;
+    }
+    for (int j = 0; j + 1 < nl; j += 2) {
+      mul_lines_s(M, ls[j], ls[j + 1]);
+      fp12s_mul(f, f, M);
+    }
+    if (nl & 1) fp12s_mul(f, f, ls[nl - 1]);
+  }
+  BN_PHASE_SYNC();
+  for (int v = 0; v < NV; v++) {
+    const V1 px = v_bcast(pv[v].x), py = v_bcast(pv[v].y);
+    V2 q1x, q1y, q2x, q2y;
+    g2_psi_s(q1x, q1y, v_bcast(qv[v].x), v_bcast(qv[v].y));
+    g2_psi_s(q2x, q2y, q1x, q1y);
+    addition_step_s(ls[v], r[v], q1x, q1y, px, py);
+    addition_step_s(ls[NV + v], r[v], q2x, v_neg(q2y), px, py);
+    if ((skip >> v) & 1) ls[v] = line_one_s(), ls[NV + v] = line_one_s();
+  }
+  for (int j = 0; j + 1 < 2 * NV; j += 2) {
+    mul_lines_s(M, ls[j], ls[j + 1]);
+    fp12s_mul(f, f, M);
+  }
 }
 
 // ------------------------------------------------------------------------------------------ full values <-> slices

@@ -315,3 +315,82 @@ int hs_trio_plonk_miller(void* vkp, const uint8_t* pf_be, uint8_t* out_be) {
   return memcmp(&want, &got, 384) ? 1 : 0;
 }
 }
+
+extern "C" {
+static int line_differs(const trio::S12& ls, const Line3& l) {
+  Fp12 got, want;
+  memset(&want, 0, sizeof want);
+  want.c0.c0 = l.x0, want.c0.c2 = l.x2, want.c1.c1 = l.x4;
+  trio::fp12s_store(got, ls);
+  return memcmp(&got, &want, 384) != 0;
+}
+static int point_differs(const trio::V2& r, const G2Jac& p) {
+  return memcmp(&r.l[0], &p.x, 64) || memcmp(&r.l[1], &p.y, 64) || memcmp(&r.l[2], &p.z, 64);
+}
+// G2 steps of the Miller loop, sliced against sequential: doubling, +Q, doubling, -Q, line product, end-point test
+// chain.  q: 128 bytes (any point of E'(Fq2)), p: 64 bytes.  Returns a bit mask of mismatching steps (0 = equal).
+int hs_trio_g2_steps(const uint8_t* q_be, const uint8_t* p_be) {
+  G2Aff q;
+  G1Aff p;
+  load_g2_unchecked(q, q_be);
+  load_g1_unchecked(p, p_be);
+  G2Jac r = to_jac(q);
+  trio::V2 rs = trio::v_const(q.x, q.y, fp2_one());
+  const trio::V1 px = trio::v_bcast(p.x), py = trio::v_bcast(p.y);
+  const trio::V2 qx = trio::v_bcast(q.x), qy = trio::v_bcast(q.y);
+  Line3 l1, l2;
+  trio::S12 s1, s2, sm;
+  int bad = 0;
+  doubling_step_at(l1, r, &p), trio::doubling_step_s(s1, rs, px, py);
+  if (line_differs(s1, l1) || point_differs(rs, r)) bad |= 1;
+  addition_step_at(l2, r, q, false, &p), trio::addition_step_s(s2, rs, qx, qy, px, py);
+  if (line_differs(s2, l2) || point_differs(rs, r)) bad |= 2;
+  Line5 m;
+  mul_lines(m, l1, l2), trio::mul_lines_s(sm, s1, s2);
+  {
+    Fp12 got, want;
+    memset(&want, 0, sizeof want);
+    want.c0.c0 = m.m0, want.c0.c1 = m.m1, want.c0.c2 = m.m2, want.c1.c0 = m.n0, want.c1.c1 = m.n1;
+    trio::fp12s_store(got, sm);
+    if (memcmp(&got, &want, 384)) bad |= 4;
+  }
+  doubling_step_at(l1, r, &p), trio::doubling_step_s(s1, rs, px, py);
+  if (line_differs(s1, l1) || point_differs(rs, r)) bad |= 8;
+  addition_step_at(l2, r, q, true, &p), trio::addition_step_s(s2, rs, qx, trio::v_neg(qy), px, py);
+  if (line_differs(s2, l2) || point_differs(rs, r)) bad |= 16;
+  return bad;
+}
+// Groth16 Miller loop (variable pair + pair table of the VK), sliced against sequential.  a: 64, b: 128, lc: 2 x 64 bytes
+// (L, C).  Returns 0 when the Fq12 value and the G2 verdict agree; *in_g2_out receives the verdict.
+int hs_trio_groth16_miller(void* vkp, const uint8_t* a_be, const uint8_t* b_be, const uint8_t* lc_be, int* in_g2_out) {
+  const Groth16VkDev& vk = *(Groth16VkDev*)vkp;
+  G1Aff a, pf[2];
+  G2Aff b;
+  load_g1_unchecked(a, a_be), load_g2_unchecked(b, b_be);
+  load_g1_unchecked(pf[0], lc_be), load_g1_unchecked(pf[1], lc_be + 64);
+  Fp12 want, got;
+  bool g_want = false, g_got = false;
+  miller_loop_pairtab<1>(want, &a, &b, pf, vk.gd_pairs, &g_want);
+  trio::S12 f;
+  trio::miller_loop_pairtab1_s(f, a, b, pf, vk.gd_pairs, &g_got);
+  trio::fp12s_store(got, f);
+  if (in_g2_out) *in_g2_out = g_got;
+  return (memcmp(&want, &got, 384) ? 1 : 0) | (g_want != g_got ? 2 : 0);
+}
+// k-pair product Miller value, sliced against sequential (skip: identity mask)
+int hs_trio_pairing_miller(int k, const uint8_t* g1, const uint8_t* g2, uint32_t skip) {
+  G1Aff p[4];
+  G2Aff q[4];
+  for (int j = 0; j < k; j++) load_g1_unchecked(p[j], g1 + 64 * j), load_g2_unchecked(q[j], g2 + 128 * j);
+  Fp12 want, got;
+  trio::S12 f;
+  switch (k) {
+    case 1: miller_loop<1, 0>(want, p, q, nullptr, nullptr, skip), trio::miller_loop_var_s<1>(f, p, q, skip); break;
+    case 2: miller_loop<2, 0>(want, p, q, nullptr, nullptr, skip), trio::miller_loop_var_s<2>(f, p, q, skip); break;
+    case 3: miller_loop<3, 0>(want, p, q, nullptr, nullptr, skip), trio::miller_loop_var_s<3>(f, p, q, skip); break;
+    default: miller_loop<4, 0>(want, p, q, nullptr, nullptr, skip), trio::miller_loop_var_s<4>(f, p, q, skip); break;
+  }
+  trio::fp12s_store(got, f);
+  return memcmp(&want, &got, 384) ? 1 : 0;
+}
+}

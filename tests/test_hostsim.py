@@ -410,3 +410,35 @@ def test_trio_final_exponentiation_and_plonk_miller(hs):
         pf = pt_bytes(g["pair_g1"][0]) + pt_bytes(g["pair_g1"][1])
         assert hs.hs_trio_plonk_miller(vk, pf, out) == 0
         assert out.raw.hex() == g["miller"]
+
+
+def test_trio_g2_steps_and_miller_loops(hs):
+    """The sliced doubling / addition steps, line products and the two Miller-loop shapes (Groth16: one variable pair
+    plus the VK pair table, with the end-point G2 verdict; raw products: k variable pairs with identity masks) give the
+    sequential code's limbs -- on points of G2 and on points of the twist outside G2."""
+    from helpers import g2_point_outside_subgroup
+    g = load_json("pairing_golden.json")
+    c = [x for x in g if x["k"] == 3][0]
+    g1, g2 = bytes.fromhex(c["g1"]), bytes.fromhex(c["g2"])
+    outside = bo.g2_to_bytes(g2_point_outside_subgroup(9))
+    for q in (g2[:128], g2[128:256], outside):
+        assert hs.hs_trio_g2_steps(q, g1[:64]) == 0
+    for x in g:
+        k = x["k"]
+        for skip in (0, 1, (1 << k) - 1) if k > 1 else (0,):
+            assert hs.hs_trio_pairing_miller(k, bytes.fromhex(x["g1"]), bytes.fromhex(x["g2"]), skip) == 0
+    case = load_json("groth16_golden.json")["cases"][0]
+    blob, n_ic = _vk_points(case)
+    hs.hs_groth16_vk_new.restype = ctypes.c_void_p
+    vk = hs.hs_groth16_vk_new(blob, n_ic)
+    hs.hs_trio_groth16_miller.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p,
+                                          ctypes.POINTER(ctypes.c_int)]
+    for pr in case["proofs"][:3]:
+        raw = bytes.fromhex(pr["proof"])
+        lc = pt_bytes(pr["L"]) + raw[192:256]
+        ing2 = ctypes.c_int(-1)
+        assert hs.hs_trio_groth16_miller(vk, raw[:64], raw[64:192], lc, ctypes.byref(ing2)) == 0
+        assert ing2.value == 1
+    ing2 = ctypes.c_int(-1)
+    assert hs.hs_trio_groth16_miller(vk, raw[:64], outside, lc, ctypes.byref(ing2)) == 0 and ing2.value == 0
+    hs.hs_groth16_vk_free(ctypes.c_void_p(vk))
