@@ -605,14 +605,38 @@ HD Fe<C> fe_inv(const Fe<C>& a) {
   return fe_pow_words(a, e);
 }
 
-// 32-byte big-endian -> plain limbs; returns false when the value is >= m (Fq::from_slice semantics).
-template <class C>
-HD bool fe_from_be_bytes(Fe<C>& out, const uint8_t* b) {
+// 32 big-endian bytes -> 8 little-endian words.  On the device a record that is 16-byte aligned (every record of a
+// 256-byte-stride Groth16 batch, the points of a pairing-product batch) is read with two 128-bit loads and one byte
+// permutation per word, a 4-byte aligned one (ragged / 904-byte PlonK records) with eight 32-bit loads, instead of
+// 32 byte loads and 24 shift-or pairs.
+HD void be32_to_words(uint32_t* w, const uint8_t* b) {
+#if defined(__CUDA_ARCH__)
+  const uintptr_t a = (uintptr_t)b;
+  if ((a & 15) == 0) {
+    const uint4 hi = *(const uint4*)b, lo = *(const uint4*)(b + 16);  // hi.x holds bytes 0..3: the top word
+    w[7] = __byte_perm(hi.x, 0, 0x0123), w[6] = __byte_perm(hi.y, 0, 0x0123);
+    w[5] = __byte_perm(hi.z, 0, 0x0123), w[4] = __byte_perm(hi.w, 0, 0x0123);
+    w[3] = __byte_perm(lo.x, 0, 0x0123), w[2] = __byte_perm(lo.y, 0, 0x0123);
+    w[1] = __byte_perm(lo.z, 0, 0x0123), w[0] = __byte_perm(lo.w, 0, 0x0123);
+    return;
+  }
+  if ((a & 3) == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = __byte_perm(*(const uint32_t*)(b + 28 - 4 * i), 0, 0x0123);
+    return;
+  }
+#endif
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     const uint8_t* p = b + 28 - 4 * i;
-    out.v[i] = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+    w[i] = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
   }
+}
+
+// 32-byte big-endian -> plain limbs; returns false when the value is >= m (Fq::from_slice semantics).
+template <class C>
+HD bool fe_from_be_bytes(Fe<C>& out, const uint8_t* b) {
+  be32_to_words(out.v, b);
   // out < m ?
   cc::sub_cc(out.v[0], C::mod(0));
   uint32_t d = 0;
