@@ -52,7 +52,10 @@ __global__ void __launch_bounds__(64)
   if (slot >= *count) return;
   int i = list[slot];
   if (i < 0) return;
-  plonk_term(work[i], *vk, proofs + stride * (size_t)i, stage, blockIdx.y);
+  // Blocks are scheduled in blockIdx order: the long terms (variable-base, ~2 200 multiplications) go first and the short
+  // ones (fixed-base tables, ~350) last, so that the short ones fill the tail instead of leaving the long ones alone on
+  // the machine at the end of the launch.
+  plonk_term(work[i], *vk, proofs + stride * (size_t)i, stage, plonk_term_order(vk->n_qcp, stage, blockIdx.y));
 }
 
 __global__ void __launch_bounds__(64)

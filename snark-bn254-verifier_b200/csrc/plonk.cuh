@@ -488,6 +488,25 @@ HD void plonk_term(PlonkWork& w, const PlonkVkDev& vk, const uint8_t* pr, int st
   w.part[t] = res;
 }
 
+// Launch order of the terms of a stage: position -> term index, variable-base terms first (see k_plonk_terms).
+//   stage 0 terms: [0, nq) BSB22 (variable) | nq + {0..3} Ql Qr Qm Qo, +4 Qk, +5 S3 (fixed) | nq + {6..9} Z H0 H1 H2 (variable)
+//   stage 1 terms: 0..2 L R O (variable) | 3 .. 4 + nq S1 S2 Qcp (fixed) | b + {0, 1, 3, 4} (variable), b + 2 g1 (fixed); b = 5 + nq
+HD int plonk_term_order(int nq, int stage, int pos) {
+  if (stage == 0) {
+    if (pos < nq) return pos;                   // BSB22
+    if (pos < nq + 4) return nq + 6 + (pos - nq);  // Z H0 H1 H2
+    return nq + (pos - nq - 4);                 // the six VK terms
+  }
+  const int b = 5 + nq;
+  if (pos < 3) return pos;                      // L R O
+  if (pos < 7) {
+    const int j = pos - 3;                      // zsH rnd, Z rnd, batchedH zeta, zsH rnd omega zeta
+    return b + (j < 2 ? j : j + 1);
+  }
+  if (pos < 7 + 2 + nq) return 3 + (pos - 7);   // S1 S2 Qcp..
+  return b + 2;                                 // g1
+}
+
 HD int plonk_stage_c(PlonkWork& w, const PlonkVkDev& vk, const uint8_t* pr, const uint8_t* rnd_be,
                      const PlonkDebug& dbg) {
   const int nq = vk.n_qcp;
