@@ -367,7 +367,8 @@ def bench_plonk(ctx, pkg, peak, work):
     if ctx.rank != 0:
         return None
     pk = peak["wide_mac_per_s"]
-    sm = work["plonk_stage_macs"]
+    joint = n >= int(os.environ.get("BN254V_PLONK_JOINT_MIN", 1 << 15))  # launch::plonk_joint_min (csrc/k_plonk.cu)
+    sm = work["plonk_joint_stage_macs" if joint else "plonk_stage_macs"]
     n_full = int((expected != 6).sum())  # survivors of stage A (6 = ERR_OPENING_POLY_MISMATCH, rejected early)
     names = ["stage_a", "terms0", "stage_c", "terms1", "stage_e"]
     sms = torch.cuda.get_device_properties(ctx.local_rank).multi_processor_count
@@ -392,7 +393,8 @@ def bench_plonk(ctx, pkg, peak, work):
                 "peak": pk / 1e12, "unit": "TMAC/s", "frac": per_stage[dom]["frac"], "traffic": ncu_traffic(kern[dom], n),
                 "share_of_step": per_stage[dom]["ms_per_launch"] / step_ms,
                 "step": {"achieved": total_macs / (step_ms * 1e-3) / 1e12, "frac": total_macs / (step_ms * 1e-3) / pk},
-                "stages": per_stage, "macs_full_path": work["plonk_full_path_macs"],
+                "stages": per_stage, "macs_full_path": sum(sm.values()),
+                "msm_form": "joint (shared doublings)" if joint else "one thread per term",
                 "proofs_reaching_the_msms": n_full}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -502,7 +504,8 @@ def bench_mixed(ctx, pkg, peak, work):
         return None
     pk = peak["wide_mac_per_s"]
     n_full = int((exp_p != 6).sum())
-    macs = work["groth16_macs"] * half + work["plonk_full_path_macs"] * n_full + \
+    pj = half >= int(os.environ.get("BN254V_PLONK_JOINT_MIN", 1 << 15))  # chunks of 2^16 proofs: the joint MSM form
+    macs = work["groth16_macs"] * half + work["plonk_joint_full_path_macs" if pj else "plonk_full_path_macs"] * n_full + \
         work["plonk_early_reject_macs"] * (half - n_full)
     ach = macs * steps / (sum(kernel_ms) * 1e-3)
     return {"metric": "mixed_items_verified_per_sec", "unit": "items/s", "value": value, "ms_per_step": dev_ms / steps,

@@ -4,6 +4,8 @@
 // verifier/src/plonk/verify.rs:46-317, verifier/src/plonk/kzg.rs:46-190).
 // `list` holds the indices of the proofs that are still alive after stage A (early rejects cost nothing further);
 // a slot is set to -(i + 1) when stage C ends the proof.
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "trio.cuh"
 
@@ -47,7 +49,7 @@ __global__ void __launch_bounds__(64)
 
 __global__ void __launch_bounds__(64)
     k_plonk_terms(const PlonkVkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride, PlonkWork* work,
-                  const int* __restrict__ list, const int* __restrict__ count, int stage) {
+                  const int* __restrict__ list, const int* __restrict__ count, int stage, int joint) {
   int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= *count) return;
   int i = list[slot];
@@ -55,17 +57,23 @@ __global__ void __launch_bounds__(64)
   // Blocks are scheduled in blockIdx order: the long terms (variable-base, ~2 200 multiplications) go first and the short
   // ones (fixed-base tables, ~350) last, so that the short ones fill the tail instead of leaving the long ones alone on
   // the machine at the end of the launch.
-  plonk_term(work[i], *vk, proofs + stride * (size_t)i, stage, plonk_term_order(vk->n_qcp, stage, blockIdx.y));
+  if (joint) {
+    // joint form (plonk.cuh plonk_item_joint): items of stage 1 in the order 0 2 3 4 1 5 (long ones first)
+    const int item = stage == 0 ? (int)blockIdx.y : ((0x514320 >> (4 * blockIdx.y)) & 15);
+    plonk_item_joint(work[i], *vk, proofs + stride * (size_t)i, stage, item);
+  } else {
+    plonk_term(work[i], *vk, proofs + stride * (size_t)i, stage, plonk_term_order(vk->n_qcp, stage, blockIdx.y));
+  }
 }
 
 __global__ void __launch_bounds__(64)
     k_plonk_stage_c(const PlonkVkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride,
                     const uint8_t* __restrict__ rnd, uint8_t* __restrict__ status, PlonkWork* work, int* list,
-                    const int* __restrict__ count, PlonkDbgPtrs dp) {
+                    const int* __restrict__ count, PlonkDbgPtrs dp, int joint) {
   int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= *count) return;
   int i = list[slot];
-  int st = plonk_stage_c(work[i], *vk, proofs + stride * (size_t)i, rnd + (size_t)32 * i, plonk_dbg(dp, i));
+  int st = plonk_stage_c(work[i], *vk, proofs + stride * (size_t)i, rnd + (size_t)32 * i, plonk_dbg(dp, i), joint != 0);
   if (st != BN254V_OK_TRUE) {
     status[i] = (uint8_t)st;
     list[slot] = -(i + 1);  // dead: the term kernel skips it, stage E walks the pairing on substitute points
@@ -78,7 +86,7 @@ template <int TPB>
 __global__ void __launch_bounds__(TPB, 1)
     k_plonk_stage_e(const PlonkVkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride,
                     uint8_t* __restrict__ status, PlonkWork* work, const int* __restrict__ list,
-                    const int* __restrict__ count, PlonkDbgPtrs dp) {
+                    const int* __restrict__ count, PlonkDbgPtrs dp, int joint) {
   const int cnt = *count;
   if ((int)(blockIdx.x * blockDim.x) >= cnt) return;  // uniform over the block
   int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -86,7 +94,7 @@ __global__ void __launch_bounds__(TPB, 1)
   int i = list[live ? slot : cnt - 1];
   if (i < 0) live = false, i = -(i + 1);
   PlonkDebug dbg = live ? plonk_dbg(dp, i) : PlonkDebug{nullptr, nullptr, nullptr, nullptr};
-  int st = plonk_stage_e(work[i], *vk, proofs + stride * (size_t)i, dbg, live);
+  int st = plonk_stage_e(work[i], *vk, proofs + stride * (size_t)i, dbg, live, joint != 0);
   if (live) status[i] = (uint8_t)st;
 }
 
@@ -96,13 +104,13 @@ __global__ void __launch_bounds__(TPB, 1)
 __global__ void __launch_bounds__(64)
     k_plonk_stage_d(const PlonkVkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride,
                     uint8_t* __restrict__ status, PlonkWork* work, int* list, const int* __restrict__ count,
-                    PlonkDbgPtrs dp) {
+                    PlonkDbgPtrs dp, int joint) {
   int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= *count) return;
   int i = list[slot];
   if (i < 0) return;
   G1Aff pf[2];
-  int st = plonk_stage_d(pf, work[i], *vk, proofs + stride * (size_t)i, plonk_dbg(dp, i));
+  int st = plonk_stage_d(pf, work[i], *vk, proofs + stride * (size_t)i, plonk_dbg(dp, i), joint != 0);
   if (st != BN254V_OK_TRUE) {
     status[i] = (uint8_t)st;
     list[slot] = -(i + 1);
@@ -143,25 +151,37 @@ int plonk_vk_prepare(cudaStream_t st, PlonkVkDev* dv, int n_fixed, G1Aff* bases_
   return 2;
 }
 
+// Joint evaluation of the MSM terms (shared doublings) once a chunk has enough proofs to fill the GPU with a third of the
+// threads; below that the per-term form wins on latency (BN254V_PLONK_JOINT_MIN overrides the switch-over point).
+static size_t plonk_joint_min() {
+  static long forced = -2;
+  if (forced == -2) {
+    const char* e = getenv("BN254V_PLONK_JOINT_MIN");
+    forced = e ? atol(e) : -1;
+  }
+  return forced >= 0 ? (size_t)forced : (size_t)1 << 15;
+}
+
 int plonk_verify(cudaStream_t st, const PlonkArgs& a, int sm_count) {
   const size_t cm = a.m;
   PlonkDbgPtrs dp{a.dbg_g1, a.dbg_fr, a.dbg_m, a.dbg_gt};
   const unsigned g64 = (unsigned)((cm + 63) / 64);
-  const int n_terms = a.n_qcp + 10;
+  const int joint = cm >= plonk_joint_min() ? 1 : 0;
+  const int n0 = plonk_n_items(a.n_qcp, 0, joint != 0), n1 = plonk_n_items(a.n_qcp, 1, joint != 0);
   cudaMemsetAsync(a.count, 0, sizeof(int), st);
   k_plonk_stage_a<<<g64, 64, 0, st>>>(a.vk, a.proofs, a.stride, a.lens, a.inputs, a.n_inputs, cm, a.status, a.work,
                                       a.list, a.count, dp);
   if (a.stage_ev) cudaEventRecord(a.stage_ev[0], st);
-  k_plonk_terms<<<dim3(g64, n_terms), 64, 0, st>>>(a.vk, a.proofs, a.stride, a.work, a.list, a.count, 0);
+  k_plonk_terms<<<dim3(g64, n0), 64, 0, st>>>(a.vk, a.proofs, a.stride, a.work, a.list, a.count, 0, joint);
   if (a.stage_ev) cudaEventRecord(a.stage_ev[1], st);
-  k_plonk_stage_c<<<g64, 64, 0, st>>>(a.vk, a.proofs, a.stride, a.rnd, a.status, a.work, a.list, a.count, dp);
+  k_plonk_stage_c<<<g64, 64, 0, st>>>(a.vk, a.proofs, a.stride, a.rnd, a.status, a.work, a.list, a.count, dp, joint);
   if (a.stage_ev) cudaEventRecord(a.stage_ev[2], st);
-  k_plonk_terms<<<dim3(g64, n_terms), 64, 0, st>>>(a.vk, a.proofs, a.stride, a.work, a.list, a.count, 1);
+  k_plonk_terms<<<dim3(g64, n1), 64, 0, st>>>(a.vk, a.proofs, a.stride, a.work, a.list, a.count, 1, joint);
   if (a.stage_ev) cudaEventRecord(a.stage_ev[3], st);
   // Three lanes per proof while one proof per thread would leave the SM sub-partitions short of warps (the number
   // of survivors is only known on the device: the choice goes by the chunk size).
   if (cm <= (size_t)trio_max_items(sm_count)) {
-    k_plonk_stage_d<<<g64, 64, 0, st>>>(a.vk, a.proofs, a.stride, a.status, a.work, a.list, a.count, dp);
+    k_plonk_stage_d<<<g64, 64, 0, st>>>(a.vk, a.proofs, a.stride, a.status, a.work, a.list, a.count, dp, joint);
     const unsigned per_block = (128 / 32) * BN_TRIOS_PER_WARP;
     k_plonk_stage_e3<128, 3><<<(unsigned)((cm + per_block - 1) / per_block), 128, trio::trio_smem_bytes(128), st>>>(
         a.vk, a.status, a.work, a.list, a.count, dp);
@@ -169,10 +189,10 @@ int plonk_verify(cudaStream_t st, const PlonkArgs& a, int sm_count) {
   }
   if (pick_shape(cm, sm_count) == SHAPE_32)
     k_plonk_stage_e<32><<<(unsigned)((cm + 31) / 32), 32, 0, st>>>(a.vk, a.proofs, a.stride, a.status, a.work, a.list,
-                                                                   a.count, dp);
+                                                                   a.count, dp, joint);
   else
     k_plonk_stage_e<128><<<(unsigned)((cm + 127) / 128), 128, 0, st>>>(a.vk, a.proofs, a.stride, a.status, a.work,
-                                                                       a.list, a.count, dp);
+                                                                       a.list, a.count, dp, joint);
   return 5;
 }
 

@@ -144,8 +144,9 @@ HD bool glv_abs(uint32_t* v) {  // two's complement -> magnitude; returns the si
 // (phi of a table entry is one multiplication by beta) with shared doublings: 132 doublings + at most 66 additions
 // instead of 252 + 64; uniform control flow across a warp apart from zero digits.  k: plain 8 x u32 LE (< r).
 // Same group element as the reference's AffineG1 * Fr; AffineG1::msm is a plain sum of such terms.
-HDN G1Jac g1_mul_w4(const G1Aff& p, const uint32_t* k) {
-  uint32_t c1[5], c2[5], k1[8], k2[8];
+// k -> (|k1|, |k2|, signs)
+HD void glv_split(uint32_t* k1, uint32_t* k2, bool& n1, bool& n2, const uint32_t* k) {
+  uint32_t c1[5], c2[5];
   {
     BN_GLV_CONST(g1, K::glv_g1)
     BN_GLV_CONST(g2, K::glv_g2)
@@ -163,29 +164,65 @@ HDN G1Jac g1_mul_w4(const G1Aff& p, const uint32_t* k) {
     glv_mac_lo(k2, c1, nb1);
     glv_mac_lo(k2, c2, nb2);
   }
-  const bool n1 = glv_abs(k1), n2 = glv_abs(k2);
-  Fp beta;
-  BN_LOAD_FP(beta, K::glv_beta, 0);
-  G1Jac tab[15];
+  n1 = glv_abs(k1), n2 = glv_abs(k2);
+}
+// tab[d - 1] = d P, d = 1..15
+HD void g1_w4_table(G1Jac* tab, const G1Aff& p) {
   tab[0] = to_jac(p);
   tab[1] = jac_double(tab[0]);
   for (int i = 2; i < 15; i++) tab[i] = jac_add_mixed(tab[i - 1], p);
+}
+// acc += [digit of k1 at nibble w] P + [digit of k2 at nibble w] phi(P)
+HD void g1_w4_add_digits(G1Jac& acc, const G1Jac* tab, const uint32_t* k1, const uint32_t* k2, bool n1, bool n2,
+                         const Fp& beta, int w) {
+  const uint32_t d1 = (k1[w >> 3] >> (4 * (w & 7))) & 15, d2 = (k2[w >> 3] >> (4 * (w & 7))) & 15;
+  if (d1) {
+    G1Jac t = tab[d1 - 1];
+    if (n1) t.y = fe_neg(t.y);
+    acc = jac_add(acc, t);
+  }
+  if (d2) {
+    G1Jac t = tab[d2 - 1];
+    t.x = fe_mul(t.x, beta);
+    if (n2) t.y = fe_neg(t.y);
+    acc = jac_add(acc, t);
+  }
+}
+HDN G1Jac g1_mul_w4(const G1Aff& p, const uint32_t* k) {
+  uint32_t k1[8], k2[8];
+  bool n1, n2;
+  glv_split(k1, k2, n1, n2, k);
+  Fp beta;
+  BN_LOAD_FP(beta, K::glv_beta, 0);
+  G1Jac tab[15];
+  g1_w4_table(tab, p);
   G1Jac acc = jac_identity<Fp>();
   for (int w = 32; w >= 0; w--) {  // 33 nibbles = 132 bits >= |k1|, |k2|
     if (w != 32)
       for (int j = 0; j < 4; j++) acc = jac_double(acc);
-    uint32_t d1 = (k1[w >> 3] >> (4 * (w & 7))) & 15, d2 = (k2[w >> 3] >> (4 * (w & 7))) & 15;
-    if (d1) {
-      G1Jac t = tab[d1 - 1];
-      if (n1) t.y = fe_neg(t.y);
-      acc = jac_add(acc, t);
-    }
-    if (d2) {
-      G1Jac t = tab[d2 - 1];
-      t.x = fe_mul(t.x, beta);
-      if (n2) t.y = fe_neg(t.y);
-      acc = jac_add(acc, t);
-    }
+    g1_w4_add_digits(acc, tab, k1, k2, n1, n2, beta, w);
+  }
+  return acc;
+}
+// sum_j [k_j] P_j for up to BN_MSM_MAX proof-supplied points, evaluated jointly (Straus): the 132 doublings are paid once
+// for the group instead of once per point.  Same group element as the sum of the separate products (AffineG1::msm sums
+// its terms; only the total is converted to affine coordinates).
+#define BN_MSM_MAX 3
+HDN G1Jac g1_msm_w4(const G1Aff* p, const uint32_t* const* k, int n) {
+  uint32_t k1[BN_MSM_MAX][8], k2[BN_MSM_MAX][8];
+  bool n1[BN_MSM_MAX], n2[BN_MSM_MAX];
+  G1Jac tab[BN_MSM_MAX][15];
+  for (int j = 0; j < n; j++) {
+    glv_split(k1[j], k2[j], n1[j], n2[j], k[j]);
+    g1_w4_table(tab[j], p[j]);
+  }
+  Fp beta;
+  BN_LOAD_FP(beta, K::glv_beta, 0);
+  G1Jac acc = jac_identity<Fp>();
+  for (int w = 32; w >= 0; w--) {
+    if (w != 32)
+      for (int j = 0; j < 4; j++) acc = jac_double(acc);
+    for (int j = 0; j < n; j++) g1_w4_add_digits(acc, tab[j], k1[j], k2[j], n1[j], n2[j], beta, w);
   }
   return acc;
 }
@@ -488,6 +525,75 @@ HD void plonk_term(PlonkWork& w, const PlonkVkDev& vk, const uint8_t* pr, int st
   w.part[t] = res;
 }
 
+// ---- joint evaluation (large batches): the terms of a stage that the verifier only ever sums are evaluated in groups
+// with shared doublings (g1_msm_w4, at most BN_MSM_MAX proof points per group) and the VK terms of a sum in one thread.
+//   stage 0 (every term goes into the linearised digest): groups of the nq + 4 proof points BSB22.. Z H0 H1 H2, then one
+//           item for Ql Qr Qm Qo Qk S3;
+//   stage 1: 0 = L R O, 1 = S1 S2 Qcp.. (both into the folded digest), 2 = zeta batchedH + (rnd omega zeta) zsH,
+//           3 = rnd zsH, 4 = rnd Z, 5 = (folded evaluations) g1.
+// The per-term form above stays for small batches, where the number of threads matters more than their work.
+HD int plonk_n_items(int nq, int stage, bool joint) {
+  if (!joint) return nq + 10;
+  return stage == 0 ? (nq + 4 + BN_MSM_MAX - 1) / BN_MSM_MAX + 1 : 6;
+}
+HD G1Jac plonk_fixed_sum(const PlonkVkDev& vk, G1Jac acc, const int* bases, const uint32_t* const* ks, int n) {
+  for (int j = 0; j < n; j++) {
+    if (vk.fixed_tables) {
+      const G1Aff* tab = vk.fixed_tables + (size_t)bases[j] * BN_IC_WINDOWS * BN_IC_ENTRIES;
+      for (int w = 0; w < BN_IC_WINDOWS; w++) {
+        const uint32_t d = (ks[j][w >> 2] >> (8 * (w & 3))) & 0xff;
+        if (d) acc = jac_add_mixed(acc, tab[w * BN_IC_ENTRIES + (d - 1)]);
+      }
+    } else {
+      acc = jac_add(acc, g1_mul_w4(plonk_fixed_base(vk, bases[j]), ks[j]));
+    }
+  }
+  return acc;
+}
+HD void plonk_item_joint(PlonkWork& w, const PlonkVkDev& vk, const uint8_t* pr, int stage, int item) {
+  const int nq = vk.n_qcp, b = 5 + nq;
+  G1Aff pts[BN_MSM_MAX];
+  const uint32_t* ks[BN_MAX_QCP + 6];
+  int bases[BN_MAX_QCP + 6];
+  G1Jac res;
+  if (stage == 0) {
+    const int nv = nq + 4, ng = (nv + BN_MSM_MAX - 1) / BN_MSM_MAX;
+    if (item < ng) {
+      int n = 0;
+      for (int v = item * BN_MSM_MAX; v < nv && n < BN_MSM_MAX; v++, n++) {
+        // proof point v: BSB22 commitment v (term v) or Z H0 H1 H2 (terms nq + 6 ..)
+        const int t = v < nq ? v : nq + 6 + (v - nq);
+        load_g1_unchecked(pts[n], v < nq ? pr + plonk_off_bsb(vk) + 64 * v : pr + 192 + 64 * (v - nq));
+        ks[n] = w.sc[t];
+      }
+      res = g1_msm_w4(pts, ks, n);
+    } else {
+      for (int j = 0; j < 4; j++) bases[j] = j, ks[j] = w.sc[nq + j];  // Ql Qr Qm Qo
+      bases[4] = 4, ks[4] = w.sc[nq + 5];                              // S3
+      res = plonk_fixed_sum(vk, to_jac(vk.qk), bases, ks, 5);           // + Qk * 1
+    }
+  } else {
+    if (item == 0) {
+      for (int j = 0; j < 3; j++) load_g1_unchecked(pts[j], pr + 64 * j), ks[j] = w.sc[j];  // L R O
+      res = g1_msm_w4(pts, ks, 3);
+    } else if (item == 1) {
+      for (int j = 0; j < 2 + nq; j++) bases[j] = 5 + j, ks[j] = w.sc[3 + j];  // S1 S2 Qcp..
+      res = plonk_fixed_sum(vk, jac_identity<Fp>(), bases, ks, 2 + nq);
+    } else if (item == 2) {
+      load_g1_unchecked(pts[0], pr + 448), ks[0] = w.sc[b + 3];                 // batchedH * zeta
+      load_g1_unchecked(pts[1], pr + plonk_off_zsh(vk)), ks[1] = w.sc[b + 4];   // zsH * (rnd omega zeta)
+      res = g1_msm_w4(pts, ks, 2);
+    } else if (item == 3) {
+      res = plonk_var(pr + plonk_off_zsh(vk), w.sc[b + 0]);                      // zsH * rnd
+    } else if (item == 4) {
+      res = plonk_var(pr + 192, w.sc[b + 1]);                                    // Z * rnd
+    } else {
+      res = plonk_fixed_or_var(vk, 7 + nq, w.sc[b + 2]);                         // g1 * folded evaluations
+    }
+  }
+  w.part[item] = res;
+}
+
 // Launch order of the terms of a stage: position -> term index, variable-base terms first (see k_plonk_terms).
 //   stage 0 terms: [0, nq) BSB22 (variable) | nq + {0..3} Ql Qr Qm Qo, +4 Qk, +5 S3 (fixed) | nq + {6..9} Z H0 H1 H2 (variable)
 //   stage 1 terms: 0..2 L R O (variable) | 3 .. 4 + nq S1 S2 Qcp (fixed) | b + {0, 1, 3, 4} (variable), b + 2 g1 (fixed); b = 5 + nq
@@ -508,10 +614,10 @@ HD int plonk_term_order(int nq, int stage, int pos) {
 }
 
 HD int plonk_stage_c(PlonkWork& w, const PlonkVkDev& vk, const uint8_t* pr, const uint8_t* rnd_be,
-                     const PlonkDebug& dbg) {
+                     const PlonkDebug& dbg, bool joint = false) {
   const int nq = vk.n_qcp;
   G1Jac acc = w.part[0];
-  for (int t = 1; t < nq + 10; t++) acc = jac_add(acc, w.part[t]);
+  for (int t = 1; t < plonk_n_items(nq, 0, joint); t++) acc = jac_add(acc, w.part[t]);
   if (!to_affine(w.lin, acc)) return BN254V_PANIC_IDENTITY;
   uint8_t lin_bytes[64];
   store_g1(lin_bytes, w.lin);
@@ -555,12 +661,16 @@ HD int plonk_stage_c(PlonkWork& w, const PlonkVkDev& vk, const uint8_t* pr, cons
 
 // The G1 side of kzg::fold and kzg::batch_verify_multi_points (plonk/kzg.rs:74-85, 128-178): sums of the term results
 // with the reference's AffineG1 conversions (an identity intermediate panics there) -> the two G1 inputs of the pairing.
-HD int plonk_stage_d(G1Aff* pf, PlonkWork& w, const PlonkVkDev& vk, const uint8_t* pr, const PlonkDebug& dbg) {
-  const int nq = vk.n_qcp, b = 5 + nq;
+HD int plonk_stage_d(G1Aff* pf, PlonkWork& w, const PlonkVkDev& vk, const uint8_t* pr, const PlonkDebug& dbg,
+                     bool joint = false) {
+  const int nq = vk.n_qcp;
+  // where the stage-1 results are: per-term form b terms of the fold, then rnd zsH, rnd Z, evals g1, and the two terms
+  // of the points-quotients sum; joint form items 0, 1 (fold), 3, 4, 5, and 2 (already summed)
+  const int n_fold = joint ? 2 : 5 + nq, b = joint ? 3 : 5 + nq;
   int st = BN254V_OK_TRUE;
   // folded digest = lin + sum gamma^i D_i (kzg::fold)
   G1Jac fd = to_jac(w.lin);
-  for (int t = 0; t < b; t++) fd = jac_add(fd, w.part[t]);
+  for (int t = 0; t < n_fold; t++) fd = jac_add(fd, w.part[t]);
   if (is_identity(fd)) st = BN254V_PANIC_IDENTITY;
   if (st == BN254V_OK_TRUE && dbg.g1) {
     G1Aff t;
@@ -578,7 +688,7 @@ HD int plonk_stage_d(G1Aff* pf, PlonkWork& w, const PlonkVkDev& vk, const uint8_
   fec.y = neg(fec.y);
   fdg = jac_add(fdg, fec);
   if (is_identity(fdg)) st = BN254V_PANIC_IDENTITY;
-  G1Jac fpq = jac_add(w.part[b + 3], w.part[b + 4]);  // zeta batchedH + rnd omega zeta zsH
+  G1Jac fpq = joint ? w.part[2] : jac_add(w.part[b + 3], w.part[b + 4]);  // zeta batchedH + rnd omega zeta zsH
   if (is_identity(fpq)) st = BN254V_PANIC_IDENTITY;
   fdg = jac_add(fdg, fpq);
   if (is_identity(fdg)) st = BN254V_PANIC_IDENTITY;
@@ -596,10 +706,11 @@ HD int plonk_stage_d(G1Aff* pf, PlonkWork& w, const PlonkVkDev& vk, const uint8_
 // `live == false`: a spare thread, or a proof that stage C already ended -- the pairing below contains block-wide
 // phase barriers, so the thread still runs it (on VK points) and its result is discarded.  For the same reason the
 // identity panics of the reference's AffineG1 conversions are recorded and the pairing runs on substitute points.
-HD int plonk_stage_e(PlonkWork& w, const PlonkVkDev& vk, const uint8_t* pr, const PlonkDebug& dbg, bool live = true) {
+HD int plonk_stage_e(PlonkWork& w, const PlonkVkDev& vk, const uint8_t* pr, const PlonkDebug& dbg, bool live = true,
+                     bool joint = false) {
   int st = live ? BN254V_OK_TRUE : BN254V_STATUS_UNSET;
   G1Aff pf[2] = {vk.g1, vk.g1};
-  if (live) st = plonk_stage_d(pf, w, vk, pr, dbg);
+  if (live) st = plonk_stage_d(pf, w, vk, pr, dbg, joint);
   const bool ok = st == BN254V_OK_TRUE;
   if (!ok) pf[0] = pf[1] = vk.g1;
   Fp12 f;
@@ -613,15 +724,21 @@ HD int plonk_stage_e(PlonkWork& w, const PlonkVkDev& vk, const uint8_t* pr, cons
 
 // All stages in one thread.
 HD int plonk_verify_one(const PlonkVkDev& vk, const uint8_t* pr, uint32_t len, const uint8_t* inputs_be, int n_inputs,
-                        const uint8_t* rnd_be, const PlonkDebug& dbg) {
+                        const uint8_t* rnd_be, const PlonkDebug& dbg, bool joint = false) {
   PlonkWork w;
   int st = plonk_stage_a(w, vk, pr, len, inputs_be, n_inputs, dbg);
   if (st != BN254V_OK_TRUE) return st;
-  for (int t = 0; t < vk.n_qcp + 10; t++) plonk_term(w, vk, pr, 0, t);
-  st = plonk_stage_c(w, vk, pr, rnd_be, dbg);
+  for (int t = 0; t < plonk_n_items(vk.n_qcp, 0, joint); t++) {
+    if (joint) plonk_item_joint(w, vk, pr, 0, t);
+    else plonk_term(w, vk, pr, 0, t);
+  }
+  st = plonk_stage_c(w, vk, pr, rnd_be, dbg, joint);
   if (st != BN254V_OK_TRUE) return st;
-  for (int t = 0; t < vk.n_qcp + 10; t++) plonk_term(w, vk, pr, 1, t);
-  return plonk_stage_e(w, vk, pr, dbg);
+  for (int t = 0; t < plonk_n_items(vk.n_qcp, 1, joint); t++) {
+    if (joint) plonk_item_joint(w, vk, pr, 1, t);
+    else plonk_term(w, vk, pr, 1, t);
+  }
+  return plonk_stage_e(w, vk, pr, dbg, true, joint);
 }
 
 }  // namespace bn254

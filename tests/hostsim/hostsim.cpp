@@ -160,10 +160,23 @@ int hs_plonk_verify(void* vk, const uint8_t* proof, uint32_t len, const uint8_t*
   PlonkDebug dbg{g1, fr, miller, gt};
   return plonk_verify_one(*(PlonkVkDev*)vk, proof, len, inputs, n_inputs, rnd, dbg);
 }
+// the same with the MSM terms of each stage evaluated jointly (shared doublings: the large-batch form)
+int hs_plonk_verify_joint(void* vk, const uint8_t* proof, uint32_t len, const uint8_t* inputs, int n_inputs,
+                          const uint8_t* rnd, uint8_t* g1, uint8_t* fr, uint8_t* miller, uint8_t* gt) {
+  PlonkDebug dbg{g1, fr, miller, gt};
+  return plonk_verify_one(*(PlonkVkDev*)vk, proof, len, inputs, n_inputs, rnd, dbg, true);
+}
 // limb multiply-adds of each stage of the staged PlonK path (the five kernels of k_plonk.cu): out[0..4] = stage A,
 // terms 0, stage C, terms 1, stage E.  Returns the final status (a proof rejected in stage A leaves out[1..4] = 0).
+int hs_plonk_stage_macs_form(void* vkp, const uint8_t* pr, uint32_t len, const uint8_t* inputs, int n_inputs,
+                             const uint8_t* rnd, unsigned long long* out, int joint);
 int hs_plonk_stage_macs(void* vkp, const uint8_t* pr, uint32_t len, const uint8_t* inputs, int n_inputs,
                         const uint8_t* rnd, unsigned long long* out) {
+  return hs_plonk_stage_macs_form(vkp, pr, len, inputs, n_inputs, rnd, out, 0);
+}
+// joint != 0: the large-batch form (MSM terms of a sum evaluated jointly)
+int hs_plonk_stage_macs_form(void* vkp, const uint8_t* pr, uint32_t len, const uint8_t* inputs, int n_inputs,
+                             const uint8_t* rnd, unsigned long long* out, int joint) {
   const PlonkVkDev& vk = *(PlonkVkDev*)vkp;
   PlonkDebug dbg{nullptr, nullptr, nullptr, nullptr};
   for (int i = 0; i < 5; i++) out[i] = 0;
@@ -173,14 +186,20 @@ int hs_plonk_stage_macs(void* vkp, const uint8_t* pr, uint32_t len, const uint8_
   int st = plonk_stage_a(w, vk, pr, len, inputs, n_inputs, dbg);
   out[0] = fe_mac_counter(), fe_mac_counter() = 0;
   if (st != BN254V_OK_TRUE) return st;
-  for (int t = 0; t < vk.n_qcp + 10; t++) plonk_term(w, vk, pr, 0, t);
+  for (int t = 0; t < plonk_n_items(vk.n_qcp, 0, joint != 0); t++) {
+    if (joint) plonk_item_joint(w, vk, pr, 0, t);
+    else plonk_term(w, vk, pr, 0, t);
+  }
   out[1] = fe_mac_counter(), fe_mac_counter() = 0;
-  st = plonk_stage_c(w, vk, pr, rnd, dbg);
+  st = plonk_stage_c(w, vk, pr, rnd, dbg, joint != 0);
   out[2] = fe_mac_counter(), fe_mac_counter() = 0;
   if (st != BN254V_OK_TRUE) return st;
-  for (int t = 0; t < vk.n_qcp + 10; t++) plonk_term(w, vk, pr, 1, t);
+  for (int t = 0; t < plonk_n_items(vk.n_qcp, 1, joint != 0); t++) {
+    if (joint) plonk_item_joint(w, vk, pr, 1, t);
+    else plonk_term(w, vk, pr, 1, t);
+  }
   out[3] = fe_mac_counter(), fe_mac_counter() = 0;
-  st = plonk_stage_e(w, vk, pr, dbg);
+  st = plonk_stage_e(w, vk, pr, dbg, true, joint != 0);
   out[4] = fe_mac_counter(), fe_mac_counter() = 0;
   return st;
 #else

@@ -179,3 +179,43 @@ def test_library_drawn_batch_opening_scalars(gpu):
     assert (st1 == gpu.OK_TRUE).all() and (st2 == gpu.OK_TRUE).all()
     seen = {d.g1[i, 2].tobytes() for d in (d1, d2) for i in range(4)}
     assert len(seen) == 8
+
+
+def test_joint_msm_form_and_thread_per_proof_pairing_on_small_inputs():
+    """Large batches evaluate the MSM terms of each sum jointly (shared doublings) and run stage E with one proof per
+    thread; small ones use one thread per term and three lanes per proof.  Forcing the large-batch forms on the bundled
+    fixtures (environment switches, read once per process -> a subprocess) must reproduce every golden intermediate and
+    the whole mutation -> status map."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = r'''
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r + "/tests"); sys.path.insert(0, %r + "/oracle")
+import __graft_entry__ as ge
+from helpers import PLONK_STATUS, load_json, plonk_fixture, plonk_vk_bytes, pt_bytes
+pkg = ge.load_package(); pkg.init(None)
+vk = plonk_vk_bytes()
+gold = load_json("plonk_golden.json")
+progs = ["fibonacci", "is-prime", "sha2", "tendermint"]
+proofs, inputs, rnds = [], [], []
+for prog in progs:
+    pr, xs = plonk_fixture(prog)
+    proofs.append(pr), inputs.append(xs), rnds.append(int(gold[prog]["rnd"], 16))
+status, dbg = pkg.PlonkVerifier.verify_batch(proofs, vk, inputs, rnd=rnds, debug=True)
+assert (status == 0).all()
+for i, prog in enumerate(progs):
+    g = gold[prog]
+    assert dbg.g1[i, 0].tobytes() == pt_bytes(g["lin_digest"]) and dbg.g1[i, 1].tobytes() == pt_bytes(g["folded_digest"])
+    assert dbg.g1[i, 2].tobytes() == pt_bytes(g["pair_g1"][0]) and dbg.g1[i, 3].tobytes() == pt_bytes(g["pair_g1"][1])
+    assert dbg.miller[i].tobytes().hex() == g["miller"] and dbg.gt[i].tobytes().hex() == g["gt"]
+muts = load_json("plonk_mutations.json")
+st = pkg.PlonkVerifier.verify_batch([bytes.fromhex(m["raw_proof"]) for m in muts], vk,
+                                    [[int(s) for s in m["inputs"]] for m in muts], rnd=[77] * len(muts))
+assert [int(s) for s in st] == [PLONK_STATUS[m["status"]] for m in muts]
+print("JOINT-OK")
+''' % (ROOT, ROOT, ROOT)
+    env = dict(os.environ, BN254V_PLONK_JOINT_MIN="0", BN254V_TRIO_MAX="0")
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=280)
+    assert "JOINT-OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]

@@ -442,3 +442,47 @@ def test_trio_g2_steps_and_miller_loops(hs):
     ing2 = ctypes.c_int(-1)
     assert hs.hs_trio_groth16_miller(vk, raw[:64], outside, lc, ctypes.byref(ing2)) == 0 and ing2.value == 0
     hs.hs_groth16_vk_free(ctypes.c_void_p(vk))
+
+
+def test_plonk_joint_msm_form_gives_the_same_values(hs):
+    """The large-batch form of the PlonK MSM rounds (terms of a sum evaluated jointly with shared doublings, VK terms of
+    a sum in one thread): bundled fixtures, other circuit shapes and mutated proofs give the same statuses and the same
+    canonical intermediates as the oracle (and hence as the per-term form)."""
+    import plonk_oracle as po
+    from helpers import PLONK_STATUS, plonk_fixture, plonk_shape_variant, plonk_vk_bytes
+    _hs_plonk(hs)
+    hs.hs_plonk_verify_joint.argtypes = hs.hs_plonk_verify.argtypes
+    vkb = plonk_vk_bytes()
+    vk = hs.hs_plonk_vk_new(vkb, len(vkb))
+    hs.hs_plonk_vk_add_tables.argtypes = [ctypes.c_void_p]
+    hs.hs_plonk_vk_add_tables(vk)  # the VK terms through the fixed-base tables, as on the device
+    gold = load_json("plonk_golden.json")
+    for prog in ("fibonacci", "tendermint"):
+        g = gold[prog]
+        pr, xs = plonk_fixture(prog)
+        inputs = b"".join(x.to_bytes(32, "big") for x in xs)
+        g1, fr, ml, gt = (ctypes.create_string_buffer(n) for n in (256, 256, 384, 384))
+        st = hs.hs_plonk_verify_joint(vk, pr, len(pr), inputs, 2, int(g["rnd"], 16).to_bytes(32, "big"), g1, fr, ml, gt)
+        assert st == 0
+        assert g1.raw[0:64] == pt_bytes(g["lin_digest"]) and g1.raw[64:128] == pt_bytes(g["folded_digest"])
+        assert g1.raw[128:192] == pt_bytes(g["pair_g1"][0]) and g1.raw[192:256] == pt_bytes(g["pair_g1"][1])
+        assert ml.raw.hex() == g["miller"] and gt.raw.hex() == g["gt"]
+    muts = [m for m in load_json("plonk_mutations.json") if m["program"] == "sha2"]
+    for m in muts:
+        pr = bytes.fromhex(m["raw_proof"])
+        inputs = b"".join(int(x).to_bytes(32, "big") for x in m["inputs"])
+        st = hs.hs_plonk_verify_joint(vk, pr, len(pr), inputs, 2, (77).to_bytes(32, "big"), None, None, None, None)
+        assert st == PLONK_STATUS[m["status"]], m["mutation"]
+    hs.hs_plonk_vk_free(vk)
+    for nq, npub in ((0, 1), (2, 3), (3, 2)):  # no fixed-base tables here: the variable-base fallback of the VK terms
+        vkb2, pr, xs = plonk_shape_variant(nq, npub)
+        d = {}
+        with pytest.raises(po.PlonkError):
+            po.plonk_verifier_verify(pr, vkb2, xs, rnd=4242, debug=d)
+        vk2 = hs.hs_plonk_vk_new(vkb2, len(vkb2))
+        inputs = b"".join(x.to_bytes(32, "big") for x in xs)
+        g1, fr, ml, gt = (ctypes.create_string_buffer(n) for n in (256, 256, 384, 384))
+        st = hs.hs_plonk_verify_joint(vk2, pr, len(pr), inputs, npub, (4242).to_bytes(32, "big"), g1, fr, ml, gt)
+        assert st == 8
+        _plonk_debug_matches_oracle(d, g1.raw, fr.raw, ml.raw, gt.raw)
+        hs.hs_plonk_vk_free(vk2)

@@ -76,6 +76,11 @@ def main(write=True):
     assert hs.hs_plonk_stage_macs(pv, pr, len(pr), inputs, 2, (77).to_bytes(32, "big"), stages) == 0
     out["plonk_stage_macs"] = {k: int(v) for k, v in zip(("stage_a", "terms0", "stage_c", "terms1", "stage_e"), stages)}
     assert sum(out["plonk_stage_macs"].values()) == out["plonk_full_path_macs"]
+    # the large-batch form: MSM terms of a sum evaluated jointly (shared doublings), chunks of >= 2^15 proofs
+    hs.hs_plonk_stage_macs_form.argtypes = hs.hs_plonk_stage_macs.argtypes + [ctypes.c_int]
+    assert hs.hs_plonk_stage_macs_form(pv, pr, len(pr), inputs, 2, (77).to_bytes(32, "big"), stages, 1) == 0
+    out["plonk_joint_stage_macs"] = {k: int(v) for k, v in zip(("stage_a", "terms0", "stage_c", "terms1", "stage_e"), stages)}
+    out["plonk_joint_full_path_macs"] = sum(out["plonk_joint_stage_macs"].values())
     bad = [m for m in load_json("plonk_mutations.json") if m["program"] == "fibonacci" and m["mutation"] == "claimed0+1"][0]
     hs.hs_mul_count(1)
     hs.hs_plonk_verify(pv, bytes.fromhex(bad["raw_proof"]), 904, inputs, 2, (77).to_bytes(32, "big"), None, None, None, None)
