@@ -45,6 +45,10 @@ HD Fp2 fp2_zero() { return Fp2{fe_zero<FpCfg>(), fe_zero<FpCfg>()}; }
 HD Fp2 fp2_one() { return Fp2{fe_one<FpCfg>(), fe_zero<FpCfg>()}; }
 HD Fp2 add(const Fp2& a, const Fp2& b) { return Fp2{fe_add(a.c0, b.c0), fe_add(a.c1, b.c1)}; }
 HD Fp2 sub(const Fp2& a, const Fp2& b) { return Fp2{fe_sub(a.c0, b.c0), fe_sub(a.c1, b.c1)}; }
+// a + b without the conditional subtractions (components < 2p).  Only valid as ONE operand of mul(Fp2, Fp2) whose other
+// operand is fully reduced: the lazy product then needs a0' b1 + a1' b0 < 4 p^2 < p 2^256 (a' < 2p, b < p), and the
+// internal operand sum a0' + a1' < 4p still fits 256 bits.  The product is the same fully reduced element.
+HD Fp2 add_nr(const Fp2& a, const Fp2& b) { return Fp2{fe_add_nr(a.c0, b.c0), fe_add_nr(a.c1, b.c1)}; }
 HD Fp2 neg(const Fp2& a) { return Fp2{fe_neg(a.c0), fe_neg(a.c1)}; }
 HD Fp2 dbl(const Fp2& a) { return Fp2{fe_dbl(a.c0), fe_dbl(a.c1)}; }
 HD Fp2 conj(const Fp2& a) { return Fp2{a.c0, fe_neg(a.c1)}; }
