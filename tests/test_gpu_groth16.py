@@ -243,3 +243,18 @@ def test_failed_proofs_inside_warps_every_launch_shape(gpu, n):
     status = gpu.Groth16Verifier.verify_batch(proofs, vk, inputs)
     bad = np.nonzero(status != expected)[0]
     assert bad.size == 0, [(int(i), gpu.status_name(status[i]), gpu.status_name(expected[i])) for i in bad[:8]]
+
+
+@pytest.mark.parametrize("stride", [256, 260, 257, 324])
+def test_record_alignment_paths(gpu, stride):
+    """Field elements are read with 128-bit loads from 16-byte aligned records (stride 256), 32-bit loads from 4-byte
+    aligned ones (260, 324 = gnark's raw proof length) and byte loads otherwise (257): same statuses, same values."""
+    n = 300
+    vk, proofs, inputs, expected = gpu.groth16_synth(99, n)
+    wide = np.zeros((n, stride), np.uint8)
+    wide[:, :256] = proofs
+    wide[:, 256:] = 0xAB  # trailing bytes of a record are ignored
+    status, dbg = gpu.Groth16Verifier.verify_batch(wide, vk, inputs, debug=True)
+    ref_status, ref_dbg = gpu.Groth16Verifier.verify_batch(proofs, vk, inputs, debug=True)
+    assert (status == expected).all() and (ref_status == expected).all()
+    assert (dbg.miller == ref_dbg.miller).all() and (dbg.gt == ref_dbg.gt).all() and (dbg.g1 == ref_dbg.g1).all()
