@@ -97,6 +97,29 @@ __device__ __forceinline__ V1 tri_sel(const V1& x0, const V1& x1, const V1& x2) 
 __device__ __forceinline__ V2 tri_sel(const V2& x0, const V2& x1, const V2& x2) {
   return V2{tri_sel(x0.c0, x1.c0, x2.c0), tri_sel(x0.c1, x1.c1, x2.c1)};
 }
+// two-way forms (one logic instruction per word): lane 0 takes x0, lanes 1 and 2 take x12 / lanes 0 and 1 take x01, lane 2 x2
+__device__ __forceinline__ V2 tri_sel_0(const V2& x0, const V2& x12) {
+  uint32_t m = lane_j() == 0 ? 0xffffffffu : 0u;
+  asm volatile("" : "+r"(m));
+  V2 r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r.c0.v[i] = x12.c0.v[i] ^ ((x0.c0.v[i] ^ x12.c0.v[i]) & m);
+    r.c1.v[i] = x12.c1.v[i] ^ ((x0.c1.v[i] ^ x12.c1.v[i]) & m);
+  }
+  return r;
+}
+__device__ __forceinline__ V2 tri_sel_2(const V2& x01, const V2& x2) {
+  uint32_t m = lane_j() == 2 ? 0xffffffffu : 0u;
+  asm volatile("" : "+r"(m));
+  V2 r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r.c0.v[i] = x01.c0.v[i] ^ ((x2.c0.v[i] ^ x01.c0.v[i]) & m);
+    r.c1.v[i] = x01.c1.v[i] ^ ((x2.c1.v[i] ^ x01.c1.v[i]) & m);
+  }
+  return r;
+}
 // true on every lane of the trio iff `ok` holds on all three
 __device__ __forceinline__ bool tri_all(bool ok) {
   const unsigned m = __ballot_sync(0xffffffffu, ok);
@@ -159,6 +182,8 @@ inline V2 tri_fetch(int s0, int s1, int s2) {
 inline V2 tri_get(const V2& x, int s0, int s1, int s2) { return V2{{x.l[s0], x.l[s1], x.l[s2]}}; }
 inline V1 tri_sel(const V1& x0, const V1& x1, const V1& x2) { return V1{{x0.l[0], x1.l[1], x2.l[2]}}; }
 inline V2 tri_sel(const V2& x0, const V2& x1, const V2& x2) { return V2{{x0.l[0], x1.l[1], x2.l[2]}}; }
+inline V2 tri_sel_0(const V2& x0, const V2& x12) { return V2{{x0.l[0], x12.l[1], x12.l[2]}}; }
+inline V2 tri_sel_2(const V2& x01, const V2& x2) { return V2{{x01.l[0], x01.l[1], x2.l[2]}}; }
 #define TRIO_FN inline
 #define TRIO_FN_NOINLINE static
 #define TRIO_EACH(expr) \
@@ -228,8 +253,8 @@ TRIO_FN_NOINLINE void fp6s_mul(V2& c, V2* vc, const V2& a, const V2& b) {
   const V2 vo = tri_fetch(0, 2, 1);  // lane 1: v2, lane 2: v1 (lane 0: unused)
   const V2 c2 = v_add(u, vo);        // meaningful on lane 2
   const V2 xw = v_xi(tri_sel(u, vo, c2));  // lane 0: xi u, lane 1: xi v2, lane 2: xi c2
-  c = tri_sel(v_add(v, xw), v_add(u, xw), c2);
-  if (vc) *vc = tri_get(tri_sel(c, c, xw), 2, 0, 1);  // (xi c2, c0, c1)
+  c = tri_sel_2(v_add(tri_sel_0(v, u), xw), c2);  // lane 0: v0 + xi u, lane 1: u + xi v2, lane 2: c2
+  if (vc) *vc = tri_get(tri_sel_2(c, xw), 2, 0, 1);  // (xi c2, c0, c1)
 }
 TRIO_FN V2 fp6s_mul(const V2& a, const V2& b) {
   V2 c;
@@ -239,7 +264,7 @@ TRIO_FN V2 fp6s_mul(const V2& a, const V2& b) {
 // v a = (xi a2, a0, a1) without a product
 TRIO_FN_NOINLINE V2 fp6s_mul_v(const V2& a) {
   const V2 r = tri_get(a, 2, 0, 1);
-  return tri_sel(v_xi(r), r, r);
+  return tri_sel_0(v_xi(r), r);
 }
 
 TRIO_FN S12 fp12s_one() {
@@ -274,8 +299,8 @@ TRIO_FN_NOINLINE void fp12s_sqr(S12& r, const S12& a) {
 // lane j holds one member in its c0 slice and fetches the other from the c1 slice of lane j + 1.
 TRIO_FN_NOINLINE void fp12s_cyclotomic_sqr(S12& r, const S12& a) {
   const V2 y = tri_get(a.c1, 1, 2, 0);         // lane 0: z1, lane 1: z5, lane 2: z2
-  const V2 za = tri_sel(a.c0, a.c0, y);        // (z0, z4, z2)
-  const V2 zb = tri_sel(y, y, a.c0);           // (z1, z5, z3)
+  const V2 za = tri_sel_2(a.c0, y);            // (z0, z4, z2)
+  const V2 zb = tri_sel_2(y, a.c0);            // (z1, z5, z3)
   // fp4_sqr: tmp = za zb, t0 = (za + zb)(za + xi zb) - tmp - xi tmp, t1 = 2 tmp
   const V2 tmp = v_mul(za, zb);
   const V2 t0 = v_sub(v_sub(v_mul(v_add(za, zb), v_add(za, v_xi(zb))), tmp), v_xi(tmp));
@@ -484,7 +509,7 @@ TRIO_FN_NOINLINE void addition_step_s(S12& line, V2& r, const V2& qx, const V2& 
   const V2 m2a = v_mul(tri_sel(d, e, e), tri_sel(d, e, qx));                       // (f = d^2, e^2, e qx)
   const V2 m2b = v_mul(tri_sel(d, v_neg(e), d), tri_sel(v_embed(py), v_embed(px), qy));  // (x4 = d py, x2 = -e px, d qy)
   const V2 x0 = v_xi(v_sub(m2a, m2b));                       // lane 2: xi (e qx - d qy)
-  tri_put(tri_sel(m2b, m2b, x0));
+  tri_put(tri_sel_2(m2b, x0));
   line = line_pack(tri_fetch(2, 2, 2), tri_fetch(0, 0, 0), tri_fetch(1, 1, 1));
   tri_put(m2a);
   const V2 ff = tri_fetch(0, 0, 0);
@@ -509,8 +534,8 @@ TRIO_FN_NOINLINE void mul_lines_s(S12& M, const S12& l1, const S12& l2) {
   tri_put(p);
   const V2 pa = tri_fetch(1, 2, 0), pb = tri_fetch(2, 0, 1);  // (p44, p22, p00), (p22, p00, p44)
   const V2 u = v_sub(v_sub(cr, p), pb);                      // lane 0: m2, lane 1: n1, lane 2: n0 / xi
-  const V2 xw = v_xi(tri_sel(pa, pa, u));                    // lane 0: xi p44, lane 1: m1 = xi p22, lane 2: n0
-  tri_put(tri_sel(u, u, xw));
+  const V2 xw = v_xi(tri_sel_2(pa, u));                      // lane 0: xi p44, lane 1: m1 = xi p22, lane 2: n0
+  tri_put(tri_sel_2(u, xw));
   const V2 g = tri_fetch(2, 2, 0);                           // lane 0: n0, lane 2: m2
   M.c0 = tri_sel(v_add(p, xw), xw, g);
   M.c1 = tri_sel(g, u, v_zero());
