@@ -111,6 +111,26 @@ int bn254v_groth16_verify_batch(const bn254v_vk* vk, const uint8_t* proofs, size
                                 const uint32_t* proof_len, const uint8_t* inputs_be, int n_inputs,
                                 size_t n, uint8_t* status, const bn254v_debug* dbg);
 
+/* OPT-IN aggregate check (no counterpart in the reference, which verifies proof by proof,
+ * verifier/src/groth16/verify.rs:65-78): "is EVERY proof of the batch valid?", for one single-pair Miller loop per
+ * proof and ONE three-pair Miller loop + final exponentiation per batch instead of a full pairing check per proof --
+ * about half the work when the answer is yes.  It CHANGES SEMANTICS and is never used by bn254v_groth16_verify_batch:
+ *   *all_valid = 1  <=>  every record is well-formed (same checks as the per-proof path: lengths, coordinates < p,
+ *                        points on their curves, B in G2, public inputs < r and != 0) AND the random linear
+ *                        combination  prod_i [e(A_i,B_i) e(L_i,gamma') e(C_i,delta') / e(alpha,beta')]^(r_i) == 1  holds.
+ *                        If all proofs are valid this always holds; if one is not, it holds with probability
+ *                        <= 2^-126 over the library's choice of the r_i (2^127 values each).
+ *   *all_valid = 0       says nothing about WHICH proof fails: call bn254v_groth16_verify_batch to find out.
+ * status (nullable): per record, the per-proof path's status if the record is malformed (PANIC_* / ERR_PREPARE_INPUTS),
+ *   BN254V_OK_TRUE if it is well-formed and went into the aggregate -- NOT a verdict on that proof.  Not reproduced:
+ *   substrate-bn's panic on an identity PARTIAL sum inside prepare_inputs (needs a discrete-log relation in the VK).
+ * rnd16: NULL in production (the library draws 16 bytes per proof from getrandom(2) AFTER it has the proofs);
+ *   n * 16 caller-supplied bytes exist for reproducible tests only -- scalars known to the prover void the check.
+ * Each device checks its own shard; the answer is the AND.                                          */
+int bn254v_groth16_batch_all_valid(const bn254v_vk* vk, const uint8_t* proofs, size_t proof_stride,
+                                   const uint32_t* proof_len, const uint8_t* inputs_be, int n_inputs,
+                                   const uint8_t* rnd16, size_t n, uint8_t* all_valid, uint8_t* status);
+
 /* rnd_be: the per-proof scalar the reference draws from OsRng inside kzg::batch_verify_multi_points
  * (verifier/src/plonk/kzg.rs:149-154).
  *   NULL (the production path): the library draws n fresh 32-byte scalars from the operating system's CSPRNG

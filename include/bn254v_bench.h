@@ -54,6 +54,9 @@ int bn254v_pairing_synth(uint64_t seed, int k, size_t first_index, size_t n, uin
 /* Dependent-free IMAD.WIDE.U32 stream on device 0: returns achieved multiply-adds per second
  * (the int32 roofline denominator).  iters >= 1.                                 */
 int bn254v_imad_peak(int iters, double* wide_mac_per_s, double* lo_mac_per_s, float* sm_clock_mhz);
+/* Test support: the host half of bn254v_groth16_batch_all_valid -- s = sum r_i and t_j = sum r_i x_ij (mod r) of m proofs
+ * as (1 + n_inputs) big-endian 32-byte scalars (r_i from the proof's 16 scalar bytes; csrc/groth16_agg.cuh).  No device. */
+void bn254v_agg_host_sums(const uint8_t* rnd16, const uint8_t* inputs_be, int n_inputs, size_t m, uint8_t* scal_be);
 /* Number of kernel launches issued by this library since init (for bench.py's gpu_launches).    */
 uint64_t bn254v_launch_count(void);
 

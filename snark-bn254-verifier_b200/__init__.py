@@ -37,14 +37,15 @@ E_BAD_ARG, E_NO_DEVICE, E_CUDA, E_VK_PARSE, E_UNSUPPORTED = -1, -2, -3, -4, -5
 EXPORTS = [
     "bn254v_init", "bn254v_shutdown", "bn254v_device_count", "bn254v_last_error", "bn254v_status_name",
     "bn254v_groth16_vk_load", "bn254v_plonk_vk_load", "bn254v_vk_free", "bn254v_vk_n_public",
-    "bn254v_groth16_verify_batch", "bn254v_plonk_verify_batch", "bn254v_pairing_product_batch",
+    "bn254v_groth16_verify_batch", "bn254v_groth16_batch_all_valid", "bn254v_plonk_verify_batch",
+    "bn254v_pairing_product_batch",
     "bn254v_vk_cache_get", "bn254v_vk_cache_size", "bn254v_vk_cache_clear", "bn254v_verify_many",
 ]
 BENCH_EXPORTS = [
     "bn254v_groth16_batch_upload", "bn254v_groth16_batch_verify", "bn254v_plonk_batch_upload",
     "bn254v_plonk_batch_verify", "bn254v_pairing_batch_upload", "bn254v_pairing_batch_verify", "bn254v_batch_free",
     "bn254v_last_stage_ms", "bn254v_last_kernel_split",
-    "bn254v_groth16_synth", "bn254v_pairing_synth", "bn254v_imad_peak", "bn254v_launch_count",
+    "bn254v_groth16_synth", "bn254v_pairing_synth", "bn254v_imad_peak", "bn254v_launch_count", "bn254v_agg_host_sums",
 ]
 
 
@@ -125,6 +126,8 @@ def load_library():
     lib.bn254v_groth16_verify_batch.argtypes = [c_void_p, u8p, c_size_t, c_void_p, u8p, c_int, c_size_t, u8p,
                                                 POINTER(_Debug)]
     lib.bn254v_groth16_verify_batch.restype = c_int
+    lib.bn254v_groth16_batch_all_valid.argtypes = [c_void_p, u8p, c_size_t, c_void_p, u8p, c_int, u8p, c_size_t, u8p, u8p]
+    lib.bn254v_groth16_batch_all_valid.restype = c_int
     lib.bn254v_plonk_verify_batch.argtypes = [c_void_p, u8p, c_size_t, c_void_p, u8p, c_int, u8p, c_size_t, u8p,
                                               POINTER(_Debug)]
     lib.bn254v_plonk_verify_batch.restype = c_int
@@ -144,6 +147,8 @@ def load_library():
     lib.bn254v_imad_peak.argtypes = [c_int, POINTER(c_double), POINTER(c_double), POINTER(c_float)]
     lib.bn254v_imad_peak.restype = c_int
     lib.bn254v_launch_count.restype = c_uint64
+    lib.bn254v_agg_host_sums.argtypes = [u8p, u8p, c_int, c_size_t, u8p]
+    lib.bn254v_agg_host_sums.restype = None
     lib.bn254v_last_kernel_split.argtypes = [POINTER(c_float), POINTER(c_float)]
     lib.bn254v_last_kernel_split.restype = c_int
     lib.bn254v_last_stage_ms.argtypes = [POINTER(c_float), c_int]
@@ -345,6 +350,27 @@ class Groth16Verifier:
         _check(lib.bn254v_groth16_verify_batch(h.ptr, _ptr(arr), arr.shape[1], _ptr(lens), _ptr(inp), k, n,
                                                _ptr(status), ctypes.byref(dbg.c) if dbg else None))
         return (status, dbg) if debug else status
+
+    @classmethod
+    def batch_all_valid(cls, proofs, vk, public_inputs, rnd16=None, want_status=False):
+        """OPT-IN aggregate check (include/bn254v.h: bn254v_groth16_batch_all_valid; no counterpart in the reference):
+        True iff every proof of the batch is valid, except with probability <= 2^-126, at about half the cost of
+        verify_batch; False says nothing about which proof fails.  `rnd16`: (n, 16) uint8 scalars for reproducible tests
+        only -- leave None so that the library draws them.  `want_status`: also return the per-record validation statuses
+        (OK_TRUE = well-formed and included in the aggregate, not a verdict)."""
+        lib = load_library()
+        h = _vk("groth16", vk, cls.sign_mode)
+        arr, lens = _pack_proofs(proofs)
+        n = arr.shape[0]
+        inp, k = _pack_inputs(public_inputs, n)
+        if rnd16 is not None:
+            rnd16 = np.ascontiguousarray(rnd16, dtype=np.uint8)
+            assert rnd16.size == 16 * n
+        status = np.full(n, STATUS_UNSET, dtype=np.uint8)
+        verdict = np.zeros(1, dtype=np.uint8)
+        _check(lib.bn254v_groth16_batch_all_valid(h.ptr, _ptr(arr), arr.shape[1], _ptr(lens), _ptr(inp), k, _ptr(rnd16), n,
+                                                  _ptr(verdict), _ptr(status)))
+        return (bool(verdict[0]), status) if want_status else bool(verdict[0])
 
 
 class PlonkVerifier:

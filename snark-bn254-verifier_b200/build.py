@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("BN254V_LIB") or os.path.join(HERE, "libbn254v.so")  # BN254V_LIB: experiment builds
 OBJ_DIR = os.path.join(HERE, "build", os.path.basename(LIB))
-SOURCES = [os.path.join(CSRC, n) for n in ("bn254v.cu", "k_groth16.cu", "k_plonk.cu", "k_pairing.cu", "k_aux.cu")]
+SOURCES = [os.path.join(CSRC, n) for n in ("bn254v.cu", "k_groth16.cu", "k_groth16_agg.cu", "k_plonk.cu", "k_pairing.cu", "k_aux.cu")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 STAMP = LIB + ".flags"  # the flags the library was built with (a flag change must trigger a rebuild too)

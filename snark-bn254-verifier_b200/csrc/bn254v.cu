@@ -209,6 +209,64 @@ int draw_rnd(std::vector<uint8_t>& out, size_t n) {
   return 0;
 }
 
+// ---- aggregate Groth16 check: the batch-wide scalars  s = sum r_i,  t_j = sum r_i x_ij  (mod r)  of one shard, with
+// r_i = a_i + b_i lambda from the proof's 16 scalar bytes (groth16_agg.cuh).  Exact integer sums of the a- and b-halves
+// (64 x 256-bit products accumulated in 384 bits), one reduction mod r at the end.
+typedef unsigned __int128 u128;
+struct Acc384 {
+  uint64_t w[6] = {0, 0, 0, 0, 0, 0};
+  void add_mul(const uint64_t* x, int nx, uint64_t k) {  // += k * x
+    uint64_t carry = 0;
+    int i = 0;
+    for (; i < nx; i++) {
+      u128 t = (u128)x[i] * k + w[i] + carry;
+      w[i] = (uint64_t)t;
+      carry = (uint64_t)(t >> 64);
+    }
+    for (; i < 6 && carry; i++) {
+      u128 t = (u128)w[i] + carry;
+      w[i] = (uint64_t)t;
+      carry = (uint64_t)(t >> 64);
+    }
+  }
+};
+Fr fr_from_acc(const Acc384& a) {  // Montgomery form of the 384-bit integer mod r
+  Fr lo, hi = fe_zero<FrCfg>(), two256;
+  for (int i = 0; i < 4; i++) lo.v[2 * i] = (uint32_t)a.w[i], lo.v[2 * i + 1] = (uint32_t)(a.w[i] >> 32);
+  for (int i = 0; i < 2; i++) hi.v[2 * i] = (uint32_t)a.w[4 + i], hi.v[2 * i + 1] = (uint32_t)(a.w[4 + i] >> 32);
+  fe_reduce_full(lo);
+  for (int i = 0; i < 8; i++) two256.v[i] = FrCfg::r1(i);  // 2^256 mod r as a plain value
+  return fe_add(fe_to_mont(lo), fe_mul(fe_to_mont(hi), fe_to_mont(two256)));
+}
+void agg_host_sums(uint8_t* scal_be, const uint8_t* rnd16, const uint8_t* inputs_be, int n_inputs, size_t m) {
+  std::vector<Acc384> acc(2 * (size_t)(1 + n_inputs));  // [a-half, b-half] of s, t_1, ..
+  const uint64_t one = 1;
+  for (size_t i = 0; i < m; i++) {
+    uint64_t a, b;
+    memcpy(&a, rnd16 + 16 * i, 8), memcpy(&b, rnd16 + 16 * i + 8, 8);  // little-endian host
+    a |= 1;
+    acc[0].add_mul(&one, 1, a);
+    acc[1].add_mul(&one, 1, b);
+    for (int j = 0; j < n_inputs; j++) {
+      const uint8_t* x = inputs_be + ((size_t)i * n_inputs + j) * 32;
+      uint64_t xw[4];
+      for (int k = 0; k < 4; k++) {
+        uint64_t t;
+        memcpy(&t, x + 24 - 8 * k, 8);
+        xw[k] = __builtin_bswap64(t);
+      }
+      acc[2 * (j + 1)].add_mul(xw, 4, a);
+      acc[2 * (j + 1) + 1].add_mul(xw, 4, b);
+    }
+  }
+  Fr lambda;
+  for (int i = 0; i < 8; i++) lambda.v[i] = K::glv_lambda(i);
+  for (int j = 0; j <= n_inputs; j++) {
+    const Fr v = fe_add(fr_from_acc(acc[2 * j]), fe_mul(lambda, fr_from_acc(acc[2 * j + 1])));
+    fe_to_be_bytes(scal_be + 32 * j, fe_from_mont(v));
+  }
+}
+
 }  // namespace
 
 struct bn254v_vk {
@@ -352,6 +410,9 @@ void bn254v_shutdown(void) {
 int bn254v_device_count(void) { return (int)g_devs.size(); }
 const char* bn254v_last_error(void) { return g_err.c_str(); }
 uint64_t bn254v_launch_count(void) { return g_launches.load(); }
+void bn254v_agg_host_sums(const uint8_t* rnd16, const uint8_t* inputs_be, int n_inputs, size_t m, uint8_t* scal_be) {
+  agg_host_sums(scal_be, rnd16, inputs_be, n_inputs, m);
+}
 
 const char* bn254v_status_name(int s) {
   switch (s) {
@@ -408,11 +469,13 @@ int bn254v_groth16_vk_load(const uint8_t* vk_bytes, size_t len, int sign_mode, b
     cudaError_t e = cudaSetDevice(d.id);
     if (e == cudaSuccess) e = cudaMalloc(&vk->dev.back(), sizeof(Groth16VkDev));
     const int n_bases = hv->n_ic - 1;
-    if (e == cudaSuccess && n_bases > 0)
-      e = cudaMalloc(&vk->aux.back(), sizeof(G1Aff) * (size_t)n_bases * BN_IC_WINDOWS * BN_IC_ENTRIES);
+    // window tables of IC_1.. (prepare_inputs), then of IC_0 and alpha (the aggregate check's batch-wide points)
+    if (e == cudaSuccess)
+      e = cudaMalloc(&vk->aux.back(), sizeof(G1Aff) * (size_t)(n_bases + 2) * BN_IC_WINDOWS * BN_IC_ENTRIES);
     Groth16VkDev* dv = (Groth16VkDev*)vk->dev.back();
     G1Aff* table = (G1Aff*)vk->aux.back();
-    hv->ic_table = table;
+    hv->ic_table = n_bases > 0 ? table : nullptr;
+    hv->agg_table = table + (size_t)n_bases * BN_IC_WINDOWS * BN_IC_ENTRIES;
     if (e == cudaSuccess) e = cudaMemcpyAsync(dv, hv, sizeof(Groth16VkDev), cudaMemcpyHostToDevice, d.stream);
     if (e == cudaSuccess) {
       g_launches += launch::groth16_vk_prepare(d.stream, dv, n_bases, table);
@@ -596,6 +659,117 @@ int bn254v_groth16_verify_batch(const bn254v_vk* vk, const uint8_t* proofs, size
     CU(cudaSetDevice(g_devs[d].id));
     CU(cudaStreamSynchronize(g_devs[d].stream));
   }
+  return BN254V_SUCCESS;
+}
+
+// ---- opt-in aggregate Groth16 check -------------------------------------------------------------
+int bn254v_groth16_batch_all_valid(const bn254v_vk* vk, const uint8_t* proofs, size_t proof_stride,
+                                   const uint32_t* proof_len, const uint8_t* inputs_be, int n_inputs,
+                                   const uint8_t* rnd16, size_t n, uint8_t* all_valid, uint8_t* status) {
+  if (!vk || vk->kind != BN254V_KIND_GROTH16 || !all_valid || (n && (!proofs || (n_inputs > 0 && !inputs_be))) ||
+      n_inputs < 0 || n_inputs > 64)
+    return fail(BN254V_E_BAD_ARG, "bad argument");
+  int rc = ensure_init();
+  if (rc) return rc;
+  *all_valid = 1;  // the empty batch
+  if (n == 0) return BN254V_SUCCESS;
+  *all_valid = 0;
+  std::vector<uint8_t> drawn;  // production path: the library draws the scalars itself, after the proofs are fixed
+  if (!rnd16) {
+    drawn.resize(n * 16);
+    size_t got = 0;
+    while (got < drawn.size()) {
+      ssize_t r = getrandom(drawn.data() + got, drawn.size() - got, 0);
+      if (r < 0) return fail(BN254V_E_BAD_ARG, "getrandom failed");
+      got += (size_t)r;
+    }
+    rnd16 = drawn.data();
+  }
+  std::vector<uint8_t> own_status;
+  if (!status) {
+    own_status.resize(n);
+    status = own_status.data();
+  }
+  const int nd = (int)g_devs.size();
+  if ((int)vk->dev.size() != nd) return fail(BN254V_E_BAD_ARG, "VK was loaded for another device set");
+  struct Part {
+    DevBuf proofs, lens, inputs, rnd, status, fbuf, gbuf, scal, scratch, verdict;
+    std::vector<uint8_t> scal_host;
+    uint8_t verdict_host = 0;
+    launch::Groth16AggArgs a;
+    size_t lo = 0, m = 0;
+  };
+  std::vector<Part> parts(nd);
+  SyncGuard guard;
+  const size_t in_bytes = (size_t)32 * n_inputs;
+  for (int d = 0; d < nd; d++) {  // per-proof half on every device
+    size_t lo, hi;
+    shard(n, d, nd, lo, hi);
+    size_t m = hi - lo;
+    if (!m) continue;
+    Part& p = parts[d];
+    p.lo = lo, p.m = m;
+    Dev& dev = g_devs[d];
+    CU(cudaSetDevice(dev.id));
+    const size_t slots = m + (m + 7) / 8;
+    CU(p.proofs.alloc(m * proof_stride));
+    CU(p.inputs.alloc(m * in_bytes));
+    CU(p.rnd.alloc(m * 16));
+    CU(p.status.alloc(m));
+    CU(p.fbuf.alloc(slots * sizeof(Fp12)));
+    CU(p.gbuf.alloc(slots * sizeof(G1Jac)));
+    CU(p.scal.alloc((size_t)32 * (1 + n_inputs)));
+    CU(p.scratch.alloc(launch::groth16_agg_scratch_bytes()));
+    CU(p.verdict.alloc(1));
+    CU(cudaMemcpyAsync(p.proofs.p, proofs + lo * proof_stride, m * proof_stride, cudaMemcpyHostToDevice, dev.stream));
+    if (in_bytes)
+      CU(cudaMemcpyAsync(p.inputs.p, inputs_be + lo * in_bytes, m * in_bytes, cudaMemcpyHostToDevice, dev.stream));
+    CU(cudaMemcpyAsync(p.rnd.p, rnd16 + lo * 16, m * 16, cudaMemcpyHostToDevice, dev.stream));
+    if (proof_len) {
+      CU(p.lens.alloc(m * 4));
+      CU(cudaMemcpyAsync(p.lens.p, proof_len + lo, m * 4, cudaMemcpyHostToDevice, dev.stream));
+    }
+    p.a = launch::Groth16AggArgs{(const Groth16VkDev*)vk->dev[d], p.proofs.as<uint8_t>(), proof_stride,
+                                 proof_len ? p.lens.as<uint32_t>() : nullptr, p.inputs.as<uint8_t>(), n_inputs,
+                                 p.rnd.as<uint8_t>(), m, p.status.as<uint8_t>(), p.fbuf.as<Fp12>(), p.gbuf.as<G1Jac>(),
+                                 p.scal.as<uint8_t>(), p.scratch.p, p.verdict.as<uint8_t>()};
+    if (d == 0) CU(cudaEventRecord(dev.ev[0], dev.stream));
+    g_launches += launch::groth16_agg_miller(dev.stream, p.a, g_sm_count);
+    CU(cudaGetLastError());
+    if (d == 0) CU(cudaEventRecord(dev.ev[1], dev.stream));
+  }
+  for (int d = 0; d < nd; d++) {  // the scalar sums (host, while the devices run), then the batch-wide half
+    Part& p = parts[d];
+    if (!p.m) continue;
+    Dev& dev = g_devs[d];
+    CU(cudaSetDevice(dev.id));
+    if (n_inputs == vk->n_public) {  // otherwise every record already carries ERR_PREPARE_INPUTS or an earlier failure
+      p.scal_host.resize((size_t)32 * (1 + n_inputs));
+      agg_host_sums(p.scal_host.data(), rnd16 + p.lo * 16, inputs_be ? inputs_be + p.lo * in_bytes : nullptr, n_inputs,
+                    p.m);
+      CU(cudaMemcpyAsync(p.scal.p, p.scal_host.data(), p.scal_host.size(), cudaMemcpyHostToDevice, dev.stream));
+      g_launches += launch::groth16_agg_finish(dev.stream, p.a);
+      CU(cudaGetLastError());
+      CU(cudaMemcpyAsync(&p.verdict_host, p.verdict.p, 1, cudaMemcpyDeviceToHost, dev.stream));
+    }
+    if (d == 0) CU(cudaEventRecord(dev.ev[2], dev.stream));
+    CU(cudaMemcpyAsync(status + p.lo, p.status.p, p.m, cudaMemcpyDeviceToHost, dev.stream));
+  }
+  for (int d = 0; d < nd; d++) {
+    CU(cudaSetDevice(g_devs[d].id));
+    CU(cudaStreamSynchronize(g_devs[d].stream));
+  }
+  if (parts[0].m) {
+    g_stage_n = 2;
+    CU(cudaEventElapsedTime(&g_stage_ms[0], g_devs[0].ev[0], g_devs[0].ev[1]));
+    CU(cudaEventElapsedTime(&g_stage_ms[1], g_devs[0].ev[1], g_devs[0].ev[2]));
+  }
+  bool all = true;
+  for (int d = 0; d < nd; d++)
+    if (parts[d].m && parts[d].verdict_host != 1) all = false;
+  for (size_t i = 0; i < n && all; i++)
+    if (status[i] != BN254V_OK_TRUE) all = false;
+  *all_valid = all ? 1 : 0;
   return BN254V_SUCCESS;
 }
 

@@ -25,6 +25,7 @@ namespace bn254 {
 struct Groth16VkDev {
   int n_ic;
   const G1Aff* ic_table;     // [n_ic - 1][BN_IC_WINDOWS][BN_IC_ENTRIES] in device memory, or null
+  const G1Aff* agg_table;    // [2][BN_IC_WINDOWS][BN_IC_ENTRIES]: the same for IC_0 and alpha (groth16_agg.cuh), or null
   G1Aff alpha;
   G2Aff beta, gamma, delta;  // already sign-adjusted (beta', gamma', delta')
   G1Aff ic[BN_MAX_IC];

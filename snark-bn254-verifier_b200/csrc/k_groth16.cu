@@ -172,9 +172,12 @@ int pick_shape(size_t m, int sm_count) {
 
 int groth16_vk_prepare(cudaStream_t st, Groth16VkDev* dv, int n_bases, G1Aff* table) {
   k_groth16_vk_prepare<<<1, 32, 0, st>>>(dv);
-  if (n_bases <= 0) return 1;
-  k_g1_fixed_tables<<<n_bases, BN_IC_WINDOWS, 0, st>>>(&dv->ic[1], table);
-  return 2;
+  if (n_bases > 0) k_g1_fixed_tables<<<n_bases, BN_IC_WINDOWS, 0, st>>>(&dv->ic[1], table);
+  // IC_0 and alpha: the batch-wide points of the aggregate check (groth16_agg.cuh)
+  G1Aff* agg = table + (size_t)n_bases * BN_IC_WINDOWS * BN_IC_ENTRIES;
+  k_g1_fixed_tables<<<1, BN_IC_WINDOWS, 0, st>>>(&dv->ic[0], agg);
+  k_g1_fixed_tables<<<1, BN_IC_WINDOWS, 0, st>>>(&dv->alpha, agg + (size_t)BN_IC_WINDOWS * BN_IC_ENTRIES);
+  return n_bases > 0 ? 4 : 3;
 }
 
 // shared with the PlonK VK preparation (k_plonk.cu has its own copy of the kernel)

@@ -1,5 +1,5 @@
 // Launch interface between the host side of the library (bn254v.cu: C ABI, sharding, buffers) and the kernel
-// translation units (k_groth16.cu, k_plonk.cu, k_pairing.cu, k_aux.cu).  Each kernel TU is compiled on its own (the
+// translation units (k_groth16.cu, k_groth16_agg.cu, k_plonk.cu, k_pairing.cu, k_aux.cu).  Each kernel TU is compiled on its own (the
 // pairing code is large; four nvcc processes in parallel build the library in a third of the time) and exposes plain
 // host functions that enqueue its kernels on a stream and return how many launches they issued.
 #pragma once
@@ -37,6 +37,27 @@ struct Groth16Args {
   cudaEvent_t mid;                  // recorded between the two launches when non-null
 };
 int groth16_verify(cudaStream_t st, const Groth16Args& a, int sm_count, bool* two_launch);
+
+// ---- opt-in aggregate Groth16 check (groth16_agg.cuh, k_groth16_agg.cu): "is every proof valid?"
+struct Groth16AggArgs {
+  const Groth16VkDev* vk;
+  const uint8_t* proofs;
+  size_t stride;
+  const uint32_t* lens;  // or null
+  const uint8_t* inputs;
+  int n_inputs;
+  const uint8_t* rnd16;  // 16 scalar bytes per proof
+  size_t m;
+  uint8_t* status;         // m per-proof validation statuses
+  Fp12* fbuf;              // m + (m + 7) / 8 entries
+  G1Jac* gbuf;             // m + (m + 7) / 8 entries
+  const uint8_t* scal_be;  // (1 + n_inputs) x 32 bytes: the host-computed scalar sums (needed by the finish half only)
+  void* scratch;           // groth16_agg_scratch_bytes()
+  uint8_t* verdict;        // 1 byte: 1 = the aggregate equation holds
+};
+size_t groth16_agg_scratch_bytes();
+int groth16_agg_miller(cudaStream_t st, const Groth16AggArgs& a, int sm_count);  // per-proof half
+int groth16_agg_finish(cudaStream_t st, const Groth16AggArgs& a);                 // trees + the batch's own pairing
 
 // ---- PlonK chunk (<= 2^16 proofs) on device-resident buffers
 struct PlonkArgs {

@@ -199,3 +199,22 @@ def twist_point_of_order(ell, rng):
         if pt is not None:
             assert bo.g2_mul_raw(pt, ell) is None
             return pt
+
+
+# ---- opt-in aggregate Groth16 check (csrc/groth16_agg.cuh)
+GLV_LAMBDA = 0xb3c4d79d41a917585bfc41088d8daaa78b17ea66b99c90dd  # (x, y) -> (beta x, y) = [lambda](x, y) on G1
+
+
+def agg_scalar(rnd16: bytes) -> int:
+    """r_i of one proof from its 16 scalar bytes: a (LE u64, made odd) + b (LE u64) * lambda mod r."""
+    a = int.from_bytes(rnd16[:8], "little") | 1
+    b = int.from_bytes(rnd16[8:16], "little")
+    return (a + b * GLV_LAMBDA) % bo.R
+
+
+def agg_batch_scalars(rnd: bytes, inputs) -> bytes:
+    """s = sum r_i and t_j = sum r_i x_ij (mod r) as 32-byte big-endian scalars: what the library's host side computes."""
+    rs = [agg_scalar(rnd[16 * i:16 * i + 16]) for i in range(len(inputs))]
+    n_in = len(inputs[0]) if inputs else 0
+    out = [sum(rs) % bo.R] + [sum(r * int(xs[j]) for r, xs in zip(rs, inputs)) % bo.R for j in range(n_in)]
+    return b"".join(v.to_bytes(32, "big") for v in out)

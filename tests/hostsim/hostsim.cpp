@@ -3,6 +3,8 @@
 // against the oracle, in a container without a GPU.  Not part of the product library.
 #include <string.h>
 
+#include <vector>
+
 #include "../../snark-bn254-verifier_b200/csrc/groth16.cuh"
 
 using namespace bn254;
@@ -411,5 +413,52 @@ int hs_trio_pairing_miller(int k, const uint8_t* g1, const uint8_t* g2, uint32_t
   }
   trio::fp12s_store(got, f);
   return memcmp(&want, &got, 384) ? 1 : 0;
+}
+}
+
+// ---- opt-in aggregate Groth16 check (csrc/groth16_agg.cuh) --------------------------------------------------------
+#include "../../snark-bn254-verifier_b200/csrc/groth16_agg.cuh"
+
+extern "C" {
+// the IC_0 / alpha window tables the CUDA vk_load builds for the aggregate check (vk from hs_groth16_vk_new*)
+void hs_groth16_vk_add_agg_tables(void* vkp) {
+  Groth16VkDev* vk = (Groth16VkDev*)vkp;
+  G1Aff* tab = new G1Aff[(size_t)2 * BN_IC_WINDOWS * BN_IC_ENTRIES];
+  for (int w = 0; w < BN_IC_WINDOWS; w++) {
+    groth16_ic_table_slice(tab + (size_t)w * BN_IC_ENTRIES, vk->ic[0], w);
+    groth16_ic_table_slice(tab + ((size_t)BN_IC_WINDOWS + w) * BN_IC_ENTRIES, vk->alpha, w);
+  }
+  vk->agg_table = tab;  // (leaked with the VK: test process)
+}
+// n records of `stride` bytes, n x n_inputs x 32 input bytes, n x 16 scalar bytes, (1 + n_inputs) x 32 batch scalars.
+// Folds in groups of `per` like the CUDA reduction kernel.  status_out[n]; f_out: n x 384 (per-proof Miller values) or
+// null.  Returns the batch verdict (1 = all valid).
+int hs_groth16_agg(void* vkp, const uint8_t* proofs, size_t stride, const uint32_t* lens, int n, const uint8_t* inputs,
+                   int n_inputs, const uint8_t* rnd16, const uint8_t* scal_be, int per, uint8_t* status_out, uint8_t* f_out) {
+  const Groth16VkDev& vk = *(Groth16VkDev*)vkp;
+  std::vector<Fp12> f(n);
+  std::vector<G1Jac> g(n);
+  bool all_ok = true;
+  for (int i = 0; i < n; i++) {
+    int st = groth16_agg_one(f[i], g[i], vk, proofs + stride * i, lens ? lens[i] : (uint32_t)stride,
+                             inputs + (size_t)32 * n_inputs * i, n_inputs, rnd16 + 16 * i);
+    status_out[i] = (uint8_t)st;
+    if (st != BN254V_OK_TRUE) all_ok = false;
+    if (f_out) fp12_to_bytes(f_out + 384 * (size_t)i, f[i]);
+  }
+  size_t cur = n;
+  while (cur > 1) {
+    size_t nxt = (cur + per - 1) / per;
+    std::vector<Fp12> f2(nxt);
+    std::vector<G1Jac> g2(nxt);
+    for (size_t t = 0; t < nxt; t++) {
+      f2[t] = f[t * per], g2[t] = g[t * per];
+      for (size_t k = t * per + 1; k < cur && k < (t + 1) * per; k++) groth16_agg_fold(f2[t], g2[t], f[k], g[k]);
+    }
+    f.swap(f2), g.swap(g2);
+    cur = nxt;
+  }
+  const bool verdict = groth16_agg_final(f[0], g[0], vk, scal_be);
+  return all_ok && verdict ? 1 : 0;
 }
 }

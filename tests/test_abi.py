@@ -72,6 +72,32 @@ def test_no_cpu_fallback(pkg):
     assert e.value.code == pkg.E_NO_DEVICE
 
 
+def test_aggregate_check_host_sums(pkg):
+    """The host half of bn254v_groth16_batch_all_valid (no device needed): s = sum r_i, t_j = sum r_i x_ij mod r."""
+    import ctypes
+    from helpers import agg_batch_scalars
+    import bn254_oracle as bo
+    lib = pkg.load_library()
+    rng = np.random.default_rng(5)
+    for n, k in ((1, 2), (7, 0), (300, 2), (1000, 3)):
+        rnd = rng.integers(0, 256, 16 * n, dtype=np.uint8)
+        xs = [[int.from_bytes(rng.bytes(32), "big") % bo.R for _ in range(k)] for _ in range(n)]
+        if n > 1 and k:
+            xs[1][0] = bo.R - 1
+            xs[0][k - 1] = (1 << 256) - 1  # not a field member: the device rejects it, the host sum must still not overflow
+            rnd[:32] = 255
+        inp = np.frombuffer(b"".join(int(x).to_bytes(32, "big") for row in xs for x in row), dtype=np.uint8)
+        out = np.zeros(32 * (1 + k), dtype=np.uint8)
+        lib.bn254v_agg_host_sums(rnd.ctypes.data, inp.ctypes.data if k else None, k, n, out.ctypes.data)
+        assert out.tobytes() == agg_batch_scalars(rnd.tobytes(), xs), (n, k)
+    with pytest.raises(pkg.LibraryError) as e:  # and the entry point itself needs a device
+        import torch
+        if torch.cuda.is_available():
+            raise pkg.LibraryError(pkg.E_NO_DEVICE, "skipped: a GPU is present")
+        pkg.Groth16Verifier.batch_all_valid([bytes(256)], bytes(10), [[1, 2]])
+    assert e.value.code in (pkg.E_NO_DEVICE, pkg.E_VK_PARSE)
+
+
 def test_product_does_not_import_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "snark-bn254-verifier_b200")):
         for f in files:

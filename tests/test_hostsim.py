@@ -486,3 +486,78 @@ def test_plonk_joint_msm_form_gives_the_same_values(hs):
         assert st == 8
         _plonk_debug_matches_oracle(d, g1.raw, fr.raw, ml.raw, gt.raw)
         hs.hs_plonk_vk_free(vk2)
+
+
+# ------------------------------------------------------------------------------------------------ aggregate Groth16 check
+def test_groth16_aggregate_check(hs):
+    """csrc/groth16_agg.cuh on the host: the per-proof Miller values are ML(r_i A_i, B_i) of the oracle, an all-valid batch
+    passes (with and without the window tables, for two fold widths), one invalid proof anywhere fails it, malformed
+    proofs keep the per-proof statuses."""
+    from helpers import agg_scalar, agg_batch_scalars
+    case = load_json("groth16_golden.json")["cases"][0]
+    td = bo.Groth16Trapdoor(case["seed"], 2, 0)
+    blob, n_ic = _vk_points(case)
+    hs.hs_groth16_vk_new.restype = ctypes.c_void_p
+    hs.hs_groth16_vk_new_tables.restype = ctypes.c_void_p
+    hs.hs_groth16_vk_add_agg_tables.argtypes = [ctypes.c_void_p]
+    hs.hs_groth16_agg.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p,
+                                  ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p]
+    vk_plain = hs.hs_groth16_vk_new(blob, n_ic)
+    vk_tab = hs.hs_groth16_vk_new_tables(blob, n_ic)
+    hs.hs_groth16_vk_add_agg_tables(vk_tab)
+    rng = np.random.default_rng(11)
+
+    def run(vk, recs, per=8, want_f=False):
+        n = len(recs)
+        stride = max(len(pb) for pb, _ in recs)
+        proofs = b"".join(pb.ljust(stride, b"\0") for pb, _ in recs)
+        lens = (ctypes.c_uint32 * n)(*[len(pb) for pb, _ in recs])
+        inputs = b"".join(int(x).to_bytes(32, "big") for _, xs in recs for x in xs)
+        rnd = rng.integers(0, 256, 16 * n, dtype=np.uint8).tobytes()
+        scal = agg_batch_scalars(rnd, [xs for _, xs in recs])
+        st = ctypes.create_string_buffer(n)
+        fo = ctypes.create_string_buffer(384 * n) if want_f else None
+        verdict = hs.hs_groth16_agg(vk, proofs, stride, lens, n, inputs, 2, rnd, scal, per, st, fo)
+        return verdict, list(st.raw), rnd, (fo.raw if want_f else None)
+
+    valid = []
+    for i in range(5):
+        pb, xs, _ = td.proof(i, corrupt=False)
+        valid.append((pb, xs))
+    verdict, st, rnd, f = run(vk_tab, valid, per=2, want_f=True)
+    assert verdict == 1 and st == [0] * 5
+    for i in (0, 3):  # per-proof Miller value = the oracle's Miller loop of (r_i A_i, B_i)
+        A = bo.uncompressed_bytes_to_g1_point(valid[i][0][:64])
+        B = bo.uncompressed_bytes_to_g2_point(valid[i][0][64:192])
+        want = bo.miller_product([(bo.g1_mul(A, agg_scalar(rnd[16 * i:16 * i + 16])), B)])
+        assert f[384 * i:384 * i + 384] == bo.fp12_to_bytes(want)
+    assert run(vk_plain, valid[:3], per=8)[0] == 1  # generic scalar multiplications instead of the tables
+    assert run(vk_tab, valid[:1])[0] == 1           # a batch of one
+    # one invalid proof (every corruption class keeps the points valid: per-proof status would be OK_FALSE)
+    for idx in range(0, 10):
+        pb, xs, ok = td.proof(idx, corrupt=True)
+        if ok:
+            continue
+        for pos in (0, 2):
+            recs = list(valid[:3])
+            recs.insert(pos, (pb, xs))
+            verdict, st, _, _ = run(vk_tab, recs, per=2)
+            assert verdict == 0 and st == [0] * 4, (idx, pos)
+    # two invalid proofs whose errors cancel without the random scalars: C_0 + D and C_1 - D
+    (p0, x0), (p1, x1) = valid[0], valid[1]
+    D = bo.g1_mul(bo.G1_GEN, 12345)
+    c0 = bo.g1_add(bo.uncompressed_bytes_to_g1_point(p0[192:256]), D)
+    c1 = bo.g1_add(bo.uncompressed_bytes_to_g1_point(p1[192:256]), bo.g1_neg(D))
+    recs = [(p0[:192] + bo.g1_to_bytes(c0), x0), (p1[:192] + bo.g1_to_bytes(c1), x1), valid[2]]
+    assert run(vk_tab, recs)[0] == 0
+    # malformed proofs: the per-proof statuses of groth16_verify_one, batch verdict 0
+    names = {"OK_TRUE": 0, "OK_FALSE": 1, "ERR_PREPARE_INPUTS": 2, "PANIC_FIELD_NOT_MEMBER": 16, "PANIC_NOT_ON_CURVE": 17,
+             "PANIC_NOT_IN_SUBGROUP": 18, "PANIC_IDENTITY": 19, "PANIC_SHORT_BUFFER": 20}
+    suite = [(name, pb, xs, want) for name, pb, xs, want in groth16_malformed_suite(td)]
+    recs = [(pb, xs) for _, pb, xs, _ in suite]
+    verdict, st, _, _ = run(vk_tab, recs)
+    assert verdict == 0
+    assert st == [names[w] for _, _, _, w in suite], [n for (n, _, _, w), s_ in zip(suite, st) if names[w] != s_]
+    # ... and the well-formed ones among them alone pass
+    good = [(pb, xs) for _, pb, xs, w in suite if w == "OK_TRUE"]
+    assert run(vk_tab, good)[0] == 1
