@@ -124,8 +124,9 @@ int bn254v_groth16_verify_batch(const bn254v_vk* vk, const uint8_t* proofs, size
  * status (nullable): per record, the per-proof path's status if the record is malformed (PANIC_* / ERR_PREPARE_INPUTS),
  *   BN254V_OK_TRUE if it is well-formed and went into the aggregate -- NOT a verdict on that proof.  Not reproduced:
  *   substrate-bn's panic on an identity PARTIAL sum inside prepare_inputs (needs a discrete-log relation in the VK).
- * rnd16: NULL in production (the library draws 16 bytes per proof from getrandom(2) AFTER it has the proofs);
- *   n * 16 caller-supplied bytes exist for reproducible tests only -- scalars known to the prover void the check.
+ * rnd16: NULL in production (AFTER it has the proofs the library draws one 32-byte seed from getrandom(2) and expands it
+ *   with ChaCha20 into 16 bytes per proof); n * 16 caller-supplied bytes exist for reproducible tests only -- scalars
+ *   known to the prover void the check.
  * Each device checks its own shard; the answer is the AND.                                          */
 int bn254v_groth16_batch_all_valid(const bn254v_vk* vk, const uint8_t* proofs, size_t proof_stride,
                                    const uint32_t* proof_len, const uint8_t* inputs_be, int n_inputs,

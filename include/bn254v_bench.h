@@ -57,6 +57,10 @@ int bn254v_imad_peak(int iters, double* wide_mac_per_s, double* lo_mac_per_s, fl
 /* Test support: the host half of bn254v_groth16_batch_all_valid -- s = sum r_i and t_j = sum r_i x_ij (mod r) of m proofs
  * as (1 + n_inputs) big-endian 32-byte scalars (r_i from the proof's 16 scalar bytes; csrc/groth16_agg.cuh).  No device. */
 void bn254v_agg_host_sums(const uint8_t* rnd16, const uint8_t* inputs_be, int n_inputs, size_t m, uint8_t* scal_be);
+/* Test support: the ChaCha20 block function (RFC 8439 2.3) and the key stream (nonce 0, counter from 0) with which the
+ * library expands one getrandom(2) seed into the per-proof scalars of bn254v_groth16_batch_all_valid.  No device.     */
+void bn254v_chacha20_block(const uint8_t* key32, uint32_t counter, const uint8_t* nonce12, uint8_t* out64);
+void bn254v_chacha20_expand(const uint8_t* key32, size_t n, uint8_t* out);
 /* Number of kernel launches issued by this library since init (for bench.py's gpu_launches).    */
 uint64_t bn254v_launch_count(void);
 

@@ -46,6 +46,7 @@ BENCH_EXPORTS = [
     "bn254v_plonk_batch_verify", "bn254v_pairing_batch_upload", "bn254v_pairing_batch_verify", "bn254v_batch_free",
     "bn254v_last_stage_ms", "bn254v_last_kernel_split",
     "bn254v_groth16_synth", "bn254v_pairing_synth", "bn254v_imad_peak", "bn254v_launch_count", "bn254v_agg_host_sums",
+    "bn254v_chacha20_block", "bn254v_chacha20_expand",
 ]
 
 
@@ -149,6 +150,10 @@ def load_library():
     lib.bn254v_launch_count.restype = c_uint64
     lib.bn254v_agg_host_sums.argtypes = [u8p, u8p, c_int, c_size_t, u8p]
     lib.bn254v_agg_host_sums.restype = None
+    lib.bn254v_chacha20_block.argtypes = [u8p, ctypes.c_uint32, u8p, u8p]
+    lib.bn254v_chacha20_block.restype = None
+    lib.bn254v_chacha20_expand.argtypes = [u8p, c_size_t, u8p]
+    lib.bn254v_chacha20_expand.restype = None
     lib.bn254v_last_kernel_split.argtypes = [POINTER(c_float), POINTER(c_float)]
     lib.bn254v_last_kernel_split.restype = c_int
     lib.bn254v_last_stage_ms.argtypes = [POINTER(c_float), c_int]

@@ -31,6 +31,8 @@ struct Dev {
   int id;
   cudaStream_t stream;
   cudaEvent_t ev[8];  // stage boundaries of the device-resident runs: ev[0] start ... ev[k] end of stage k
+  cudaStream_t side;  // second stream and its two ordering events (aggregate Groth16 check)
+  cudaEvent_t side_ev[2];
 };
 
 std::mutex g_mu;
@@ -177,6 +179,7 @@ struct SyncGuard {
     for (auto& d : g_devs) {
       cudaSetDevice(d.id);
       cudaStreamSynchronize(d.stream);
+      cudaStreamSynchronize(d.side);
     }
   }
 };
@@ -207,6 +210,45 @@ int draw_rnd(std::vector<uint8_t>& out, size_t n) {
     while (is_zero_mod_r(out.data() + 32 * i))
       if (getrandom(out.data() + 32 * i, 32, 0) != 32) return fail(BN254V_E_BAD_ARG, "getrandom failed");
   return 0;
+}
+
+// ---- ChaCha20 (RFC 8439 block function): expands one 32-byte getrandom(2) seed into the per-proof scalars of the
+// aggregate Groth16 check (getrandom itself delivers ~0.4 GB/s: 40 ms for 2^20 proofs, on the critical path).
+inline uint32_t rotl32(uint32_t x, int k) { return (x << k) | (x >> (32 - k)); }
+void chacha20_block(uint8_t out[64], const uint8_t key[32], uint32_t counter, const uint8_t nonce[12]) {
+  uint32_t st[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u};
+  memcpy(st + 4, key, 32);  // little-endian host
+  st[12] = counter;
+  memcpy(st + 13, nonce, 12);
+  uint32_t x[16];
+  memcpy(x, st, 64);
+#define BN_QR(a, b, c, d)                          \
+  x[a] += x[b], x[d] = rotl32(x[d] ^ x[a], 16);    \
+  x[c] += x[d], x[b] = rotl32(x[b] ^ x[c], 12);    \
+  x[a] += x[b], x[d] = rotl32(x[d] ^ x[a], 8);     \
+  x[c] += x[d], x[b] = rotl32(x[b] ^ x[c], 7);
+  for (int r = 0; r < 10; r++) {
+    BN_QR(0, 4, 8, 12) BN_QR(1, 5, 9, 13) BN_QR(2, 6, 10, 14) BN_QR(3, 7, 11, 15)
+    BN_QR(0, 5, 10, 15) BN_QR(1, 6, 11, 12) BN_QR(2, 7, 8, 13) BN_QR(3, 4, 9, 14)
+  }
+#undef BN_QR
+  for (int i = 0; i < 16; i++) x[i] += st[i];
+  memcpy(out, x, 64);
+}
+// out[0, n) = the ChaCha20 key stream of `key` with nonce (0, 0, block >> 32) and counter = block (low 32 bits)
+void chacha20_expand(uint8_t* out, size_t n, const uint8_t key[32]) {
+  uint8_t nonce[12] = {0};
+  uint8_t blk[64];
+  for (size_t off = 0, b = 0; off < n; off += 64, b++) {
+    const uint32_t hi = (uint32_t)(b >> 32);
+    memcpy(nonce + 8, &hi, 4);
+    if (n - off >= 64) {
+      chacha20_block(out + off, key, (uint32_t)b, nonce);
+    } else {
+      chacha20_block(blk, key, (uint32_t)b, nonce);
+      memcpy(out + off, blk, n - off);
+    }
+  }
 }
 
 // ---- aggregate Groth16 check: the batch-wide scalars  s = sum r_i,  t_j = sum r_i x_ij  (mod r)  of one shard, with
@@ -386,6 +428,8 @@ int bn254v_init(const int* devices, int n_devices) {
     CU(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, id));
     CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
     for (auto& ev : d.ev) CU(cudaEventCreate(&ev));
+    CU(cudaStreamCreateWithFlags(&d.side, cudaStreamNonBlocking));
+    for (auto& ev : d.side_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     g_devs.push_back(d);
   }
   g_inited = true;
@@ -401,6 +445,9 @@ void bn254v_shutdown(void) {
     DevBuf::pool_release(d.id);
     cudaStreamDestroy(d.stream);
     for (auto& ev : d.ev) cudaEventDestroy(ev);
+    cudaStreamSynchronize(d.side);
+    cudaStreamDestroy(d.side);
+    for (auto& ev : d.side_ev) cudaEventDestroy(ev);
   }
   PinnedBuf::release_all();
   g_devs.clear();
@@ -410,6 +457,10 @@ void bn254v_shutdown(void) {
 int bn254v_device_count(void) { return (int)g_devs.size(); }
 const char* bn254v_last_error(void) { return g_err.c_str(); }
 uint64_t bn254v_launch_count(void) { return g_launches.load(); }
+void bn254v_chacha20_block(const uint8_t* key32, uint32_t counter, const uint8_t* nonce12, uint8_t* out64) {
+  chacha20_block(out64, key32, counter, nonce12);
+}
+void bn254v_chacha20_expand(const uint8_t* key32, size_t n, uint8_t* out) { chacha20_expand(out, n, key32); }
 void bn254v_agg_host_sums(const uint8_t* rnd16, const uint8_t* inputs_be, int n_inputs, size_t m, uint8_t* scal_be) {
   agg_host_sums(scal_be, rnd16, inputs_be, n_inputs, m);
 }
@@ -674,15 +725,24 @@ int bn254v_groth16_batch_all_valid(const bn254v_vk* vk, const uint8_t* proofs, s
   *all_valid = 1;  // the empty batch
   if (n == 0) return BN254V_SUCCESS;
   *all_valid = 0;
-  std::vector<uint8_t> drawn;  // production path: the library draws the scalars itself, after the proofs are fixed
-  if (!rnd16) {
-    drawn.resize(n * 16);
-    size_t got = 0;
-    while (got < drawn.size()) {
-      ssize_t r = getrandom(drawn.data() + got, drawn.size() - got, 0);
-      if (r < 0) return fail(BN254V_E_BAD_ARG, "getrandom failed");
-      got += (size_t)r;
+  // production path: the library draws the scalars itself, after the proofs are fixed -- one 32-byte seed from the
+  // operating system's CSPRNG, expanded with ChaCha20 on a helper thread while the proofs travel to the devices
+  std::vector<uint8_t> drawn;
+  std::thread drawer;
+  struct Joiner {
+    std::thread& t;
+    ~Joiner() {
+      if (t.joinable()) t.join();
     }
+  } joiner{drawer};
+  if (!rnd16) {
+    uint8_t seed[32];
+    if (getrandom(seed, sizeof seed, 0) != (ssize_t)sizeof seed) return fail(BN254V_E_BAD_ARG, "getrandom failed");
+    drawn.resize(n * 16);
+    uint8_t* dst = drawn.data();
+    const size_t bytes = drawn.size();
+    std::vector<uint8_t> key(seed, seed + 32);
+    drawer = std::thread([dst, bytes, key] { chacha20_expand(dst, bytes, key.data()); });
     rnd16 = drawn.data();
   }
   std::vector<uint8_t> own_status;
@@ -697,12 +757,13 @@ int bn254v_groth16_batch_all_valid(const bn254v_vk* vk, const uint8_t* proofs, s
     std::vector<uint8_t> scal_host;
     uint8_t verdict_host = 0;
     launch::Groth16AggArgs a;
+    Fp12* product = nullptr;
     size_t lo = 0, m = 0;
   };
   std::vector<Part> parts(nd);
   SyncGuard guard;
   const size_t in_bytes = (size_t)32 * n_inputs;
-  for (int d = 0; d < nd; d++) {  // per-proof half on every device
+  for (int d = 0; d < nd; d++) {  // buffers and the proofs' way to the devices
     size_t lo, hi;
     shard(n, d, nd, lo, hi);
     size_t m = hi - lo;
@@ -711,7 +772,7 @@ int bn254v_groth16_batch_all_valid(const bn254v_vk* vk, const uint8_t* proofs, s
     p.lo = lo, p.m = m;
     Dev& dev = g_devs[d];
     CU(cudaSetDevice(dev.id));
-    const size_t slots = m + (m + 7) / 8;
+    const size_t slots = launch::groth16_agg_slots(m);
     CU(p.proofs.alloc(m * proof_stride));
     CU(p.inputs.alloc(m * in_bytes));
     CU(p.rnd.alloc(m * 16));
@@ -724,31 +785,47 @@ int bn254v_groth16_batch_all_valid(const bn254v_vk* vk, const uint8_t* proofs, s
     CU(cudaMemcpyAsync(p.proofs.p, proofs + lo * proof_stride, m * proof_stride, cudaMemcpyHostToDevice, dev.stream));
     if (in_bytes)
       CU(cudaMemcpyAsync(p.inputs.p, inputs_be + lo * in_bytes, m * in_bytes, cudaMemcpyHostToDevice, dev.stream));
-    CU(cudaMemcpyAsync(p.rnd.p, rnd16 + lo * 16, m * 16, cudaMemcpyHostToDevice, dev.stream));
     if (proof_len) {
       CU(p.lens.alloc(m * 4));
       CU(cudaMemcpyAsync(p.lens.p, proof_len + lo, m * 4, cudaMemcpyHostToDevice, dev.stream));
     }
+  }
+  if (drawer.joinable()) drawer.join();  // the scalars are complete
+  for (int d = 0; d < nd; d++) {
+    Part& p = parts[d];
+    if (!p.m) continue;
+    const size_t lo = p.lo, m = p.m;
+    Dev& dev = g_devs[d];
+    CU(cudaSetDevice(dev.id));
+    CU(cudaMemcpyAsync(p.rnd.p, rnd16 + lo * 16, m * 16, cudaMemcpyHostToDevice, dev.stream));
     p.a = launch::Groth16AggArgs{(const Groth16VkDev*)vk->dev[d], p.proofs.as<uint8_t>(), proof_stride,
                                  proof_len ? p.lens.as<uint32_t>() : nullptr, p.inputs.as<uint8_t>(), n_inputs,
                                  p.rnd.as<uint8_t>(), m, p.status.as<uint8_t>(), p.fbuf.as<Fp12>(), p.gbuf.as<G1Jac>(),
                                  p.scal.as<uint8_t>(), p.scratch.p, p.verdict.as<uint8_t>()};
     if (d == 0) CU(cudaEventRecord(dev.ev[0], dev.stream));
-    g_launches += launch::groth16_agg_miller(dev.stream, p.a, g_sm_count);
+    g_launches += launch::groth16_agg_c(dev.stream, p.a);
+    CU(cudaEventRecord(dev.side_ev[0], dev.stream));
+    g_launches += launch::groth16_agg_miller(dev.stream, p.a, g_sm_count, &p.product);
     CU(cudaGetLastError());
     if (d == 0) CU(cudaEventRecord(dev.ev[1], dev.stream));
   }
-  for (int d = 0; d < nd; d++) {  // the scalar sums (host, while the devices run), then the batch-wide half
+  const bool shape_ok = n_inputs == vk->n_public;  // otherwise every record carries ERR_PREPARE_INPUTS or an earlier failure
+  for (int d = 0; d < nd; d++) {  // the scalar sums (host, while the devices run), then the batch's own pairing
     Part& p = parts[d];
     if (!p.m) continue;
     Dev& dev = g_devs[d];
     CU(cudaSetDevice(dev.id));
-    if (n_inputs == vk->n_public) {  // otherwise every record already carries ERR_PREPARE_INPUTS or an earlier failure
+    if (shape_ok) {
       p.scal_host.resize((size_t)32 * (1 + n_inputs));
       agg_host_sums(p.scal_host.data(), rnd16 + p.lo * 16, inputs_be ? inputs_be + p.lo * in_bytes : nullptr, n_inputs,
                     p.m);
-      CU(cudaMemcpyAsync(p.scal.p, p.scal_host.data(), p.scal_host.size(), cudaMemcpyHostToDevice, dev.stream));
-      g_launches += launch::groth16_agg_finish(dev.stream, p.a);
+      // side stream: needs the [r_i] C_i of this device (side_ev[0]) and the sums; runs underneath the Miller kernel
+      CU(cudaStreamWaitEvent(dev.side, dev.side_ev[0], 0));
+      CU(cudaMemcpyAsync(p.scal.p, p.scal_host.data(), p.scal_host.size(), cudaMemcpyHostToDevice, dev.side));
+      g_launches += launch::groth16_agg_side(dev.side, p.a);
+      CU(cudaEventRecord(dev.side_ev[1], dev.side));
+      CU(cudaStreamWaitEvent(dev.stream, dev.side_ev[1], 0));
+      g_launches += launch::groth16_agg_final(dev.stream, p.a, p.product);
       CU(cudaGetLastError());
       CU(cudaMemcpyAsync(&p.verdict_host, p.verdict.p, 1, cudaMemcpyDeviceToHost, dev.stream));
     }
@@ -758,6 +835,7 @@ int bn254v_groth16_batch_all_valid(const bn254v_vk* vk, const uint8_t* proofs, s
   for (int d = 0; d < nd; d++) {
     CU(cudaSetDevice(g_devs[d].id));
     CU(cudaStreamSynchronize(g_devs[d].stream));
+    CU(cudaStreamSynchronize(g_devs[d].side));
   }
   if (parts[0].m) {
     g_stage_n = 2;

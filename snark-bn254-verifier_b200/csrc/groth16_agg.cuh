@@ -7,6 +7,8 @@
 // final-exponentiates to 1, where  sum r_i L_i = (sum r_i) IC_0 + sum_j (sum_i r_i x_ij) IC_{j+1}.
 // So a proof costs two short scalar multiplications and ONE single-pair Miller loop (instead of a three-pair loop and
 // a final exponentiation), and the batch costs a product tree, a three-pair Miller loop and one final exponentiation.
+// The [r_i] C_i come first, in their own cheap pass: then the sum tree, the batch's three points and its Miller loop
+// (a handful of threads) run on a second stream underneath the proofs' Miller loops instead of after them.
 //
 // r_i = a_i + b_i lambda with a_i (odd), b_i uniform 64-bit: (a, b) -> a + b lambda is injective on that box (the
 // shortest vector of the GLV lattice is ~2^127), so r_i is uniform over 2^127 distinct non-zero values of Fr, and
@@ -70,31 +72,34 @@ HD int groth16_agg_parse_one(G1Aff& A, G2Aff& B, G1Aff& C, const Groth16VkDev& v
   return st;
 }
 
-// One proof's share: f = ML(r A, B), rc = [r] C.  A proof that fails validation (or a spare thread, `live == false`)
-// contributes f = 1 and rc = O and walks the loop on substitute VK points (block-wide barriers inside).
-HD int groth16_agg_one(Fp12& f, G1Jac& rc, const Groth16VkDev& vk, const uint8_t* proof, uint32_t proof_len,
+// One proof's shares.  (1) rc = [r_i] C_i -- or O when the record is short or C is not a curve point (the proof then
+// fails validation in (2) anyway).  Separate from (2) so that the batch's own pairing, which needs sum rc, can run
+// while the Miller loops of the proofs are still going.
+HD G1Jac groth16_agg_c_one(const uint8_t* proof, uint32_t proof_len, const uint8_t* rnd16) {
+  G1Aff C;
+  if (proof_len < 256 || load_g1_checked(C, proof + 192) != BN254V_OK_TRUE) return jac_identity<Fp>();
+  uint32_t a[2], b[2];
+  groth16_agg_scalar(a, b, rnd16);
+  return g1_mul_glv64(C, a, b);
+}
+// (2) f = ML(r_i A_i, B_i).  A proof that fails validation (or a spare thread, `live == false`) contributes f = 1 and
+// walks the loop on substitute VK points (block-wide barriers inside).
+HD int groth16_agg_one(Fp12& f, const Groth16VkDev& vk, const uint8_t* proof, uint32_t proof_len,
                        const uint8_t* inputs_be, int n_inputs, const uint8_t* rnd16, bool live = true) {
   G1Aff A, C;
   G2Aff B;
   int st = groth16_agg_parse_one(A, B, C, vk, proof, proof_len, inputs_be, n_inputs, live);
   const bool ok = st == BN254V_OK_TRUE;
-  if (!ok) A = vk.alpha, B = vk.beta, C = vk.ic[0];
+  if (!ok) A = vk.alpha, B = vk.beta;
   uint32_t a[2], b[2];
   groth16_agg_scalar(a, b, rnd16);
-  rc = g1_mul_glv64(C, a, b);
   G1Aff rA;
   to_affine(rA, g1_mul_glv64(A, a, b));  // A has order r and r_i != 0: never the identity
   bool in_g2;
   miller_loop<1, 0>(f, &rA, &B, nullptr, nullptr, 0, &in_g2);
   if (ok && !in_g2) st = BN254V_PANIC_NOT_IN_SUBGROUP;
-  if (st != BN254V_OK_TRUE) f = fp12_one(), rc = jac_identity<Fp>();
+  if (st != BN254V_OK_TRUE) f = fp12_one();
   return st;
-}
-
-// One step of the product / sum trees: (f, g) <- (f * f2, g + g2)
-HD void groth16_agg_fold(Fp12& f, G1Jac& g, const Fp12& f2, const G1Jac& g2) {
-  mul(f, f, f2);
-  g = jac_add(g, g2);
 }
 
 // The batch's own three pairs: (-(s) alpha, beta'), (s IC_0 + sum t_j IC_j, gamma'), (sum r_i C_i, delta').
@@ -128,14 +133,18 @@ HD bool groth16_agg_points(G1Aff& nsa, G1Aff& sl, G1Aff& sc, const Groth16VkDev&
   return true;
 }
 
-// The whole batch verdict from the folded product F and sum (one thread; the CUDA path runs the same steps on three
-// lanes: k_groth16_agg_final3).
-HD bool groth16_agg_final(const Fp12& F, const G1Jac& sum_rc, const Groth16VkDev& vk, const uint8_t* scal_be) {
+// The batch's own three-pair Miller value f' (false: degenerate batch, see groth16_agg_points), and the verdict from it
+// and the folded product F of the proofs' Miller values.  (One thread; the CUDA path runs the same steps on three lanes:
+// k_groth16_agg_fprime3 / k_groth16_agg_final3.)
+HD bool groth16_agg_fprime(Fp12& fp, const G1Jac& sum_rc, const Groth16VkDev& vk, const uint8_t* scal_be) {
   G1Aff nsa, pf[2];
   if (!groth16_agg_points(nsa, pf[0], pf[1], vk, scal_be, sum_rc)) return false;
+  miller_loop_pairtab<1>(fp, &nsa, &vk.beta, pf, vk.gd_pairs, nullptr);
+  return true;
+}
+HD bool groth16_agg_final(const Fp12& F, const Fp12& fp) {
   Fp12 f;
-  miller_loop_pairtab<1>(f, &nsa, &vk.beta, pf, vk.gd_pairs, nullptr);
-  mul(f, f, F);
+  mul(f, F, fp);
   final_exponentiation(f, f);
   return eq(f, fp12_one());
 }

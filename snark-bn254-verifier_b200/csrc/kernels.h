@@ -49,15 +49,20 @@ struct Groth16AggArgs {
   const uint8_t* rnd16;  // 16 scalar bytes per proof
   size_t m;
   uint8_t* status;         // m per-proof validation statuses
-  Fp12* fbuf;              // m + (m + 7) / 8 entries
-  G1Jac* gbuf;             // m + (m + 7) / 8 entries
-  const uint8_t* scal_be;  // (1 + n_inputs) x 32 bytes: the host-computed scalar sums (needed by the finish half only)
+  Fp12* fbuf;              // groth16_agg_slots(m) entries
+  G1Jac* gbuf;             // groth16_agg_slots(m) entries
+  const uint8_t* scal_be;  // (1 + n_inputs) x 32 bytes: the host-computed scalar sums (read by the side stream only)
   void* scratch;           // groth16_agg_scratch_bytes()
   uint8_t* verdict;        // 1 byte: 1 = the aggregate equation holds
 };
 size_t groth16_agg_scratch_bytes();
-int groth16_agg_miller(cudaStream_t st, const Groth16AggArgs& a, int sm_count);  // per-proof half
-int groth16_agg_finish(cudaStream_t st, const Groth16AggArgs& a);                 // trees + the batch's own pairing
+size_t groth16_agg_slots(size_t m);
+// main stream: _c, then _miller (-> where the product of the Miller values lands), then -- after the side stream --
+// _final; side stream, after _c: _side (sum tree, the batch's points and its own Miller value)
+int groth16_agg_c(cudaStream_t st, const Groth16AggArgs& a);
+int groth16_agg_side(cudaStream_t st, const Groth16AggArgs& a);
+int groth16_agg_miller(cudaStream_t st, const Groth16AggArgs& a, int sm_count, Fp12** product);
+int groth16_agg_final(cudaStream_t st, const Groth16AggArgs& a, const Fp12* product);
 
 // ---- PlonK chunk (<= 2^16 proofs) on device-resident buffers
 struct PlonkArgs {

@@ -440,25 +440,27 @@ int hs_groth16_agg(void* vkp, const uint8_t* proofs, size_t stride, const uint32
   std::vector<G1Jac> g(n);
   bool all_ok = true;
   for (int i = 0; i < n; i++) {
-    int st = groth16_agg_one(f[i], g[i], vk, proofs + stride * i, lens ? lens[i] : (uint32_t)stride,
-                             inputs + (size_t)32 * n_inputs * i, n_inputs, rnd16 + 16 * i);
+    const uint32_t len = lens ? lens[i] : (uint32_t)stride;
+    g[i] = groth16_agg_c_one(proofs + stride * i, len, rnd16 + 16 * i);
+    int st = groth16_agg_one(f[i], vk, proofs + stride * i, len, inputs + (size_t)32 * n_inputs * i, n_inputs, rnd16 + 16 * i);
     status_out[i] = (uint8_t)st;
     if (st != BN254V_OK_TRUE) all_ok = false;
     if (f_out) fp12_to_bytes(f_out + 384 * (size_t)i, f[i]);
   }
   size_t cur = n;
-  while (cur > 1) {
+  while (cur > 1) {  // the shape of the CUDA trees: `per` to one per pass
     size_t nxt = (cur + per - 1) / per;
     std::vector<Fp12> f2(nxt);
     std::vector<G1Jac> g2(nxt);
     for (size_t t = 0; t < nxt; t++) {
       f2[t] = f[t * per], g2[t] = g[t * per];
-      for (size_t k = t * per + 1; k < cur && k < (t + 1) * per; k++) groth16_agg_fold(f2[t], g2[t], f[k], g[k]);
+      for (size_t k = t * per + 1; k < cur && k < (t + 1) * per; k++) mul(f2[t], f2[t], f[k]), g2[t] = jac_add(g2[t], g[k]);
     }
     f.swap(f2), g.swap(g2);
     cur = nxt;
   }
-  const bool verdict = groth16_agg_final(f[0], g[0], vk, scal_be);
+  Fp12 fp;
+  const bool verdict = groth16_agg_fprime(fp, g[0], vk, scal_be) && groth16_agg_final(f[0], fp);
   return all_ok && verdict ? 1 : 0;
 }
 }

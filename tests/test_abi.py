@@ -98,6 +98,32 @@ def test_aggregate_check_host_sums(pkg):
     assert e.value.code in (pkg.E_NO_DEVICE, pkg.E_VK_PARSE)
 
 
+def test_chacha20_expansion_of_the_scalar_seed(pkg):
+    """RFC 8439 2.3.2 block vector; the key stream the library expands its getrandom seed with = counter-mode blocks."""
+    lib = pkg.load_library()
+    key = np.arange(32, dtype=np.uint8)
+    nonce = np.frombuffer(bytes.fromhex("000000090000004a00000000"), dtype=np.uint8).copy()
+    out = np.zeros(64, dtype=np.uint8)
+    lib.bn254v_chacha20_block(key.ctypes.data, 1, nonce.ctypes.data, out.ctypes.data)
+    assert out.tobytes().hex() == ("10f1e7e4d13b5915500fdd1fa32071c4c7d1f4c733c068030422aa9ac3d46c4e"
+                                   "d2826446079faa0914c2d705d98b02a2b5129cd1de164eb9cbd083e8a2503c4e")
+    zero = np.zeros(12, dtype=np.uint8)
+    for n in (0, 1, 63, 64, 65, 1000):
+        got = np.zeros(n + 1, dtype=np.uint8)
+        got[n] = 0xA5  # guard byte
+        lib.bn254v_chacha20_expand(key.ctypes.data, n, got.ctypes.data)
+        want = b""
+        for b in range((n + 63) // 64):
+            lib.bn254v_chacha20_block(key.ctypes.data, b, zero.ctypes.data, out.ctypes.data)
+            want += out.tobytes()
+        assert got[:n].tobytes() == want[:n] and got[n] == 0xA5
+    a, b = np.zeros(256, np.uint8), np.zeros(256, np.uint8)
+    lib.bn254v_chacha20_expand(key.ctypes.data, 256, a.ctypes.data)
+    key[0] ^= 1
+    lib.bn254v_chacha20_expand(key.ctypes.data, 256, b.ctypes.data)
+    assert (a != b).sum() > 200
+
+
 def test_product_does_not_import_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "snark-bn254-verifier_b200")):
         for f in files:
