@@ -35,6 +35,8 @@ import sys
 import threading
 import time
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -54,7 +56,7 @@ def parse_args():
     ap.add_argument("--pairing-batch", type=int, default=1 << 20, help="4-pair sets per GPU per step")
     ap.add_argument("--mixed-total", type=int, default=1 << 22, help="items of the mixed workload over ALL GPUs")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workloads", default="groth16,plonk,pairing,mixed,single",
+    ap.add_argument("--workloads", default="groth16,plonk,pairing,mixed,single,allvalid",
                     help="comma list: groth16 (always), plonk, pairing, mixed, single (in-library multi-device, N > 1)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="proofs in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -343,6 +345,59 @@ def bench_groth16(ctx, pkg, peak, work):
             "cpu_inputs": (vk, proofs, inputs, expected)}
 
 
+def bench_all_valid(ctx, pkg, peak, work):
+    """Opt-in aggregate check (bn254v_groth16_batch_all_valid) on an all-valid batch of the headline size: the valid half
+    of 2 x batch trapdoor proofs.  Through the C ABI with host buffers (there is no device-resident form): `value` is
+    from the device time of the call (CUDA events inside the library), `e2e` from the wall clock around it."""
+    args, n, world = ctx.args, ctx.args.batch, ctx.world
+    torch = ctx.torch
+    vk, proofs, inputs, expected = pkg.groth16_synth(SEED + 1, 2 * n, first_index=ctx.rank * 2 * n)
+    keep = expected == pkg.OK_TRUE
+    assert int(keep.sum()) == n
+    t_proofs = torch.from_numpy(np.ascontiguousarray(proofs[keep])).pin_memory()
+    t_inputs = torch.from_numpy(np.ascontiguousarray(inputs[keep])).pin_memory()
+    vp, vi = t_proofs.numpy(), t_inputs.numpy()
+    ver = pkg.Groth16Verifier
+    for _ in range(max(2, args.warmup)):
+        assert ver.batch_all_valid(vp, vk, vi) is True
+    ctx.barrier()
+    dev_ms, tail_ms = 0.0, 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.flush_l2()
+        ok = ver.batch_all_valid(vp, vk, vi)
+        ms = pkg.last_stage_ms()
+        dev_ms += ms[0] + ms[1]
+        tail_ms += ms[1]
+        assert ok is True
+    ctx.barrier()
+    e2e_s = ctx.max_over_ranks(time.perf_counter() - t0)
+    dev_ms = ctx.max_over_ranks(dev_ms)
+    # one corrupted member: the answer flips
+    vp[n // 3] = proofs[np.flatnonzero(~keep)[0]]
+    vi[n // 3] = inputs[np.flatnonzero(~keep)[0]]
+    assert ver.batch_all_valid(vp, vk, vi) is False
+    if ctx.rank != 0:
+        return None
+    macs = work.get("groth16_agg_macs", 0)
+    pk = peak["wide_mac_per_s"]
+    achieved = macs * n * args.steps / ((dev_ms - tail_ms) * 1e-3) if macs else None
+    return {"metric": "groth16_proofs_checked_per_sec_all_valid_batches", "unit": UNIT,
+            "value": world * n * args.steps / (dev_ms * 1e-3), "ms_per_step": dev_ms / args.steps, "steps": args.steps,
+            "scaling": "weak",
+            "config": {"workload": "2^%d VALID trapdoor Groth16 proofs per GPU (the valid half of 2^%d); opt-in aggregate check "
+                                   "'is every proof valid?' (bn254v_groth16_batch_all_valid, scalars drawn by the library); "
+                                   "each GPU answers for its own shard" % (n.bit_length() - 1, n.bit_length()),
+                       "proofs_per_gpu": n},
+            "e2e": {"value": world * n * args.steps / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": vp.nbytes + vi.nbytes + 16 * n, "d2h_bytes_per_step": n + 1},
+            "roofline": {"bound": "int32-imad", "kernel": "k_groth16_agg_c + k_groth16_agg_miller (+ product tree)",
+                         "achieved": achieved / 1e12 if achieved else None, "peak": pk / 1e12, "unit": "TMAC/s",
+                         "frac": achieved / pk if achieved else None, "traffic": None, "macs_per_proof": macs,
+                         "batch_tail_ms": tail_ms / args.steps},
+            "note": "changes semantics (one answer per batch, soundness error <= 2^-126): never used by verify_batch"}
+
+
 def bench_plonk(ctx, pkg, peak, work):
     """configs[2]: `--plonk-batch` proofs per GPU (4 bundled SP1 proofs replicated, 50 % mutated: half of the mutated
     ones are rejected before the MSMs, the other half in the final pairing check)."""
@@ -582,6 +637,8 @@ def run_b200(args):
         extra["pairing"] = bench_pairing(ctx, pkg, peak, work)
     if "mixed" in wl:
         extra["mixed"] = bench_mixed(ctx, pkg, peak, work)
+    if "allvalid" in wl:
+        extra["all_valid"] = bench_all_valid(ctx, pkg, peak, work)
     total_launches = pkg.launch_count()
     if ctx.rank != 0:
         if ctx.dist is not None:

@@ -3,7 +3,7 @@
 //! BN254V_LIB_DIR instead (what `python snark-bn254-verifier_b200/build.py` produces).
 use std::{env, path::PathBuf, process::Command};
 
-const SOURCES: [&str; 5] = ["bn254v.cu", "k_groth16.cu", "k_plonk.cu", "k_pairing.cu", "k_aux.cu"];
+const SOURCES: [&str; 6] = ["bn254v.cu", "k_groth16.cu", "k_groth16_agg.cu", "k_plonk.cu", "k_pairing.cu", "k_aux.cu"];
 
 fn main() {
     let root = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap()).join("..");

@@ -58,6 +58,10 @@ extern "C" {
         vk: *const bn254v_vk, proofs: *const u8, proof_stride: usize, proof_len: *const u32, inputs_be: *const u8,
         n_inputs: i32, n: usize, status: *mut u8, dbg: *const bn254v_debug,
     ) -> i32;
+    pub fn bn254v_groth16_batch_all_valid(
+        vk: *const bn254v_vk, proofs: *const u8, proof_stride: usize, proof_len: *const u32, inputs_be: *const u8,
+        n_inputs: i32, rnd16: *const u8, n: usize, all_valid: *mut u8, status: *mut u8,
+    ) -> i32;
     pub fn bn254v_plonk_verify_batch(
         vk: *const bn254v_vk, proofs: *const u8, proof_stride: usize, proof_len: *const u32, inputs_be: *const u8,
         n_inputs: i32, rnd_be: *const u8, n: usize, status: *mut u8, dbg: *const bn254v_debug,

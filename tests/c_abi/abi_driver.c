@@ -57,6 +57,23 @@ int main(void) {
   }
   CHECK(n_true == N / 2);
 
+  /* opt-in aggregate check: yes for the valid half packed together, no for the whole (half-corrupted) batch */
+  {
+    static uint8_t vproofs[N * 256], vinputs[N * 64];
+    int nv = 0;
+    for (int i = 0; i < N; i++)
+      if (expected[i] == BN254V_OK_TRUE) {
+        memcpy(vproofs + 256 * nv, proofs + 256 * i, 256);
+        memcpy(vinputs + 64 * nv, inputs + 64 * i, 64);
+        nv++;
+      }
+    uint8_t yes = 7, no = 7;
+    CHECK(bn254v_groth16_batch_all_valid(h1, vproofs, 256, NULL, vinputs, 2, NULL, nv, &yes, NULL) == 0);
+    CHECK(bn254v_groth16_batch_all_valid(h1, proofs, 256, NULL, inputs, 2, NULL, N, &no, status) == 0);
+    CHECK(yes == 1 && no == 0);
+    for (int i = 0; i < N; i++) CHECK(status[i] == BN254V_OK_TRUE); /* well-formed, in the aggregate: not a verdict */
+  }
+
   /* ragged records: the second one is cut short */
   uint32_t lens[3] = {256, 100, 256};
   CHECK(bn254v_groth16_verify_batch(h1, proofs, 256, lens, inputs, 2, 3, status, NULL) == 0);

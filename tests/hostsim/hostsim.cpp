@@ -430,6 +430,22 @@ void hs_groth16_vk_add_agg_tables(void* vkp) {
   }
   vk->agg_table = tab;  // (leaked with the VK: test process)
 }
+// multiply-adds of one proof's share of the aggregate check: [r] C, then validation + [r] A + the single-pair Miller loop
+unsigned long long hs_groth16_agg_proof_macs(void* vkp, const uint8_t* proof, uint32_t len, const uint8_t* inputs, int n_inputs,
+                                             const uint8_t* rnd16, unsigned long long* c_part) {
+#ifdef BN254_COUNT_MULS
+  const unsigned long long before = fe_mac_counter();
+  G1Jac g = groth16_agg_c_one(proof, len, rnd16);
+  const unsigned long long mid = fe_mac_counter();
+  Fp12 f;
+  groth16_agg_one(f, *(Groth16VkDev*)vkp, proof, len, inputs, n_inputs, rnd16);
+  (void)g;
+  if (c_part) *c_part = mid - before;
+  return fe_mac_counter() - before;
+#else
+  return 0;
+#endif
+}
 // n records of `stride` bytes, n x n_inputs x 32 input bytes, n x 16 scalar bytes, (1 + n_inputs) x 32 batch scalars.
 // Folds in groups of `per` like the CUDA reduction kernel.  status_out[n]; f_out: n x 384 (per-proof Miller values) or
 // null.  Returns the batch verdict (1 = all valid).

@@ -50,6 +50,19 @@ def main(write=True):
     hs.hs_final_exp_only(bytes.fromhex(c["miller"]))
     out["groth16_finish_macs"] = hs.hs_mul_count(1)
     out["groth16_miller_macs"] = out["groth16_macs"] - out["groth16_finish_macs"]
+    # opt-in aggregate check (csrc/groth16_agg.cuh): one proof's share = [r] C | validation, [r] A, single-pair Miller loop
+    hs.hs_groth16_agg_proof_macs.restype = ctypes.c_ulonglong
+    hs.hs_groth16_agg_proof_macs.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_int,
+                                             ctypes.c_char_p, ctypes.POINTER(ctypes.c_ulonglong)]
+    tot = cpart = 0
+    for i, pr in enumerate(case["proofs"]):
+        inputs = b"".join(int(x).to_bytes(32, "big") for x in pr["inputs"])
+        cp = ctypes.c_ulonglong(0)
+        rnd = bytes((37 * i + 11 * k + 5) & 255 for k in range(16))
+        tot += hs.hs_groth16_agg_proof_macs(h, bytes.fromhex(pr["proof"]), 256, inputs, 2, rnd, ctypes.byref(cp))
+        cpart += cp.value
+    out["groth16_agg_macs"] = tot // n
+    out["groth16_agg_c_macs"] = cpart // n
     # raw pairing products
     for c in load_json("pairing_golden.json"):
         if c["is_one"]:
