@@ -1,4 +1,10 @@
-# A/B of experiment builds: every altlibs/*.so, then the in-tree library (default bench headline fields)
-for l in altlibs/*.so snark-bn254-verifier_b200/libbn254v.so; do echo $l; BN254V_LIB=$PWD/$l timeout 300 python bench.py --steps 10 --warmup 3 2>/dev/null | tail -1 | python -c "
+# A/B of experiment builds: every altlibs/*.so (built with BN254V_LIB=... BN254V_NVCC_EXTRA=... python build.py), then the
+# in-tree library.  The extra flags are read back from the .flags stamp so that the staleness check accepts the build.
+# Usage: bash tools/probe/ab.sh [extra bench.py flags]
+for l in altlibs/*.so snark-bn254-verifier_b200/libbn254v.so; do
+  extra=$(sed 's/.*-fPIC//' $l.flags 2>/dev/null)
+  echo "$l [$extra]"
+  BN254V_LIB=$PWD/$l BN254V_NVCC_EXTRA="$extra" timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-secondary "$@" 2>/dev/null | tail -1 | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print('step ms', d['ms_per_step'], 'proofs/s', d['value'], 'miller', d['roofline']['kernel_ms_per_launch'], 'finish', d['roofline']['step']['finish_ms_per_launch'], 'plonk ms', d['plonk']['ms'], 'plonk 2^17 proofs/s', d['plonk']['e2e_proofs_per_sec_2e17_batch'], 'pp4 ms', d['pairing_product_k4']['ms'], 'e2e', d['e2e']['value'])"; done
+d=json.loads(sys.stdin.read()); r=d['roofline']
+print('step ms', d['ms_per_step'], 'proofs/s', d['value'], 'miller', r['kernel_ms_per_launch'], 'finish', r['step']['finish_ms_per_launch'], 'frac', r['frac'])"; done
