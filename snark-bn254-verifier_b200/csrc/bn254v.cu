@@ -656,9 +656,12 @@ void bn254v_vk_cache_clear(void) {
 }
 
 // ---- Groth16 batch -----------------------------------------------------------------------------
-int bn254v_groth16_verify_batch(const bn254v_vk* vk, const uint8_t* proofs, size_t proof_stride,
-                                const uint32_t* proof_len, const uint8_t* inputs_be, int n_inputs, size_t n,
-                                uint8_t* status, const bn254v_debug* dbg) {
+// The batch entry points share the per-device streams, events and stage timers: calls from several host threads are
+// serialised by g_call_mu in the exported wrappers (end of this block); the *_impl bodies are what
+// bn254v_verify_many's helper thread calls while that call holds the lock.
+static int groth16_verify_batch_impl(const bn254v_vk* vk, const uint8_t* proofs, size_t proof_stride,
+                                     const uint32_t* proof_len, const uint8_t* inputs_be, int n_inputs, size_t n,
+                                     uint8_t* status, const bn254v_debug* dbg) {
   if (!vk || vk->kind != BN254V_KIND_GROTH16 || !status || (n && (!proofs || (n_inputs > 0 && !inputs_be))) ||
       n_inputs < 0 || n_inputs > 64)
     return fail(BN254V_E_BAD_ARG, "bad argument");
@@ -714,9 +717,9 @@ int bn254v_groth16_verify_batch(const bn254v_vk* vk, const uint8_t* proofs, size
 }
 
 // ---- opt-in aggregate Groth16 check -------------------------------------------------------------
-int bn254v_groth16_batch_all_valid(const bn254v_vk* vk, const uint8_t* proofs, size_t proof_stride,
-                                   const uint32_t* proof_len, const uint8_t* inputs_be, int n_inputs,
-                                   const uint8_t* rnd16, size_t n, uint8_t* all_valid, uint8_t* status) {
+static int groth16_batch_all_valid_impl(const bn254v_vk* vk, const uint8_t* proofs, size_t proof_stride,
+                                        const uint32_t* proof_len, const uint8_t* inputs_be, int n_inputs,
+                                        const uint8_t* rnd16, size_t n, uint8_t* all_valid, uint8_t* status) {
   if (!vk || vk->kind != BN254V_KIND_GROTH16 || !all_valid || (n && (!proofs || (n_inputs > 0 && !inputs_be))) ||
       n_inputs < 0 || n_inputs > 64)
     return fail(BN254V_E_BAD_ARG, "bad argument");
@@ -851,9 +854,9 @@ int bn254v_groth16_batch_all_valid(const bn254v_vk* vk, const uint8_t* proofs, s
   return BN254V_SUCCESS;
 }
 
-int bn254v_plonk_verify_batch(const bn254v_vk* vk, const uint8_t* proofs, size_t proof_stride,
-                              const uint32_t* proof_len, const uint8_t* inputs_be, int n_inputs,
-                              const uint8_t* rnd_be, size_t n, uint8_t* status, const bn254v_debug* dbg) {
+static int plonk_verify_batch_impl(const bn254v_vk* vk, const uint8_t* proofs, size_t proof_stride,
+                                   const uint32_t* proof_len, const uint8_t* inputs_be, int n_inputs,
+                                   const uint8_t* rnd_be, size_t n, uint8_t* status, const bn254v_debug* dbg) {
   if (!vk || vk->kind != BN254V_KIND_PLONK || !status || (n && (!proofs || (n_inputs > 0 && !inputs_be))) ||
       n_inputs < 0 || n_inputs > BN_MAX_PLONK_PUBLIC)
     return fail(BN254V_E_BAD_ARG, "bad argument");
@@ -925,8 +928,8 @@ int bn254v_plonk_verify_batch(const bn254v_vk* vk, const uint8_t* proofs, size_t
 }
 
 // ---- raw pairing products ----------------------------------------------------------------------
-int bn254v_pairing_product_batch(const uint8_t* g1, const uint8_t* g2, int k, size_t n, uint8_t* is_one,
-                                 uint8_t* miller_out, uint8_t* gt_out) {
+static int pairing_product_batch_impl(const uint8_t* g1, const uint8_t* g2, int k, size_t n, uint8_t* is_one,
+                                      uint8_t* miller_out, uint8_t* gt_out) {
   if (k < 1 || k > 4 || !is_one || (n && (!g1 || !g2))) return fail(BN254V_E_BAD_ARG, "bad argument");
   int rc = ensure_init();
   if (rc) return rc;
@@ -969,7 +972,7 @@ int bn254v_pairing_product_batch(const uint8_t* g1, const uint8_t* g2, int k, si
 // ---- mixed batches -----------------------------------------------------------------------------
 // Items are grouped by (kind, VK, n_inputs); each group is packed into one contiguous host batch (ragged proofs keep
 // their own length) and goes through the batch entry points above; statuses are scattered back in item order.
-int bn254v_verify_many(const bn254v_item* items, size_t n, int sign_mode, const uint8_t* rnd_be, uint8_t* status) {
+static int verify_many_impl(const bn254v_item* items, size_t n, int sign_mode, const uint8_t* rnd_be, uint8_t* status) {
   if ((n && !items) || !status || (sign_mode != 0 && sign_mode != 1)) return fail(BN254V_E_BAD_ARG, "bad argument");
   int rc = ensure_init();
   if (rc) return rc;
@@ -1096,11 +1099,11 @@ int bn254v_verify_many(const bn254v_item* items, size_t n, int sign_mode, const 
   auto run = [&](Stage* sg) {
     Group& gr = *sg->t.gr;
     if (gr.kind == BN254V_KIND_GROTH16)
-      sg->rc = bn254v_groth16_verify_batch(gr.vk, sg->proofs.as<uint8_t>(), gr.stride,
+      sg->rc = groth16_verify_batch_impl(gr.vk, sg->proofs.as<uint8_t>(), gr.stride,
                                            gr.ragged ? sg->lens.as<uint32_t>() : nullptr, sg->inputs.as<uint8_t>(),
                                            gr.n_inputs, sg->t.m, sg->st.as<uint8_t>(), nullptr);
     else
-      sg->rc = bn254v_plonk_verify_batch(gr.vk, sg->proofs.as<uint8_t>(), gr.stride,
+      sg->rc = plonk_verify_batch_impl(gr.vk, sg->proofs.as<uint8_t>(), gr.stride,
                                          gr.ragged ? sg->lens.as<uint32_t>() : nullptr, sg->inputs.as<uint8_t>(),
                                          gr.n_inputs, sg->has_rnd ? sg->rnd.as<uint8_t>() : nullptr, sg->t.m,
                                          sg->st.as<uint8_t>(), nullptr);
@@ -1130,6 +1133,36 @@ int bn254v_verify_many(const bn254v_item* items, size_t n, int sign_mode, const 
     if (!result) result = r2;
   }
   return result;
+}
+
+// ---- the exported batch entry points: one call at a time -------------------------------------------------------
+static std::mutex g_call_mu;
+int bn254v_groth16_verify_batch(const bn254v_vk* vk, const uint8_t* proofs, size_t proof_stride,
+                                const uint32_t* proof_len, const uint8_t* inputs_be, int n_inputs, size_t n,
+                                uint8_t* status, const bn254v_debug* dbg) {
+  std::lock_guard<std::mutex> lk(g_call_mu);
+  return groth16_verify_batch_impl(vk, proofs, proof_stride, proof_len, inputs_be, n_inputs, n, status, dbg);
+}
+int bn254v_groth16_batch_all_valid(const bn254v_vk* vk, const uint8_t* proofs, size_t proof_stride,
+                                   const uint32_t* proof_len, const uint8_t* inputs_be, int n_inputs,
+                                   const uint8_t* rnd16, size_t n, uint8_t* all_valid, uint8_t* status) {
+  std::lock_guard<std::mutex> lk(g_call_mu);
+  return groth16_batch_all_valid_impl(vk, proofs, proof_stride, proof_len, inputs_be, n_inputs, rnd16, n, all_valid, status);
+}
+int bn254v_plonk_verify_batch(const bn254v_vk* vk, const uint8_t* proofs, size_t proof_stride,
+                              const uint32_t* proof_len, const uint8_t* inputs_be, int n_inputs,
+                              const uint8_t* rnd_be, size_t n, uint8_t* status, const bn254v_debug* dbg) {
+  std::lock_guard<std::mutex> lk(g_call_mu);
+  return plonk_verify_batch_impl(vk, proofs, proof_stride, proof_len, inputs_be, n_inputs, rnd_be, n, status, dbg);
+}
+int bn254v_pairing_product_batch(const uint8_t* g1, const uint8_t* g2, int k, size_t n, uint8_t* is_one,
+                                 uint8_t* miller_out, uint8_t* gt_out) {
+  std::lock_guard<std::mutex> lk(g_call_mu);
+  return pairing_product_batch_impl(g1, g2, k, n, is_one, miller_out, gt_out);
+}
+int bn254v_verify_many(const bn254v_item* items, size_t n, int sign_mode, const uint8_t* rnd_be, uint8_t* status) {
+  std::lock_guard<std::mutex> lk(g_call_mu);
+  return verify_many_impl(items, n, sign_mode, rnd_be, status);
 }
 
 // ---- device-resident batches (bn254v_bench.h) ----------------------------------------------------
@@ -1245,6 +1278,7 @@ int bn254v_pairing_batch_upload(const uint8_t* g1, const uint8_t* g2, int k, siz
 
 // runs the staged batch on every device; stage events on device slot 0
 static int batch_run(const bn254v_vk* vk, bn254v_batch* b, uint8_t* status, float* kernel_ms) {
+  std::lock_guard<std::mutex> call_lock(g_call_mu);
   const int nd = (int)g_devs.size();
   if ((int)b->parts.size() != nd) return fail(BN254V_E_BAD_ARG, "batch was staged for another device set");
   if (vk && (int)vk->dev.size() != nd) return fail(BN254V_E_BAD_ARG, "VK was loaded for another device set");

@@ -58,3 +58,44 @@ def test_mixed_batch_config5_parity(gpu):
     assert (status[0::2][idx] == st_c).all()
     _, st_c = ref_cpu.plonk_verify_batch(vk_p, pr_p[idx], in_p[idx], rnd_p[idx], threads=os.cpu_count() or 1)
     assert (status[1::2][idx] == st_c).all()
+
+
+def test_calls_from_several_host_threads(gpu):
+    """The batch entry points share per-device streams and scratch pools: concurrent callers are serialised inside the
+    library and every caller gets its own batch's answers."""
+    import threading
+    import workloads
+    vk_p = workloads.plonk_vk_bytes()
+    jobs = []
+    for t in range(4):
+        vk, proofs, inputs, expected = gpu.groth16_synth(100 + t, 3000 + 500 * t)
+        jobs.append(("groth16", vk, proofs, inputs, None, expected))
+    pp, pi, pr, pe = workloads.plonk_workload(512, seed=9)
+    jobs.append(("plonk", vk_p, pp, pi, pr, pe))
+    g1, g2, e1 = gpu.pairing_synth(5, 2000, k=2)
+    jobs.append(("pairing", None, g1, g2, None, e1))
+    results, errors = [None] * len(jobs), []
+
+    def work(j):
+        try:
+            kind, vk, a, b, rnd, _ = jobs[j]
+            for _ in range(3):
+                if kind == "groth16":
+                    results[j] = gpu.Groth16Verifier.verify_batch(a, vk, b)
+                    keep = results[j] == gpu.OK_TRUE
+                    assert gpu.Groth16Verifier.batch_all_valid(np.ascontiguousarray(a[keep]), vk, np.ascontiguousarray(b[keep])) is True
+                elif kind == "plonk":
+                    results[j] = gpu.PlonkVerifier.verify_batch(a, vk, b, rnd=rnd)
+                else:
+                    results[j] = gpu.pairing_product_batch(a, b, 2)
+        except Exception as e:  # surfaced in the main thread
+            errors.append((j, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(j,)) for j in range(len(jobs))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for (kind, *_rest, expected), got in zip(jobs, results):
+        assert (np.asarray(got) == expected).all(), kind
