@@ -134,8 +134,9 @@ int bn254v_groth16_batch_all_valid(const bn254v_vk* vk, const uint8_t* proofs, s
 
 /* rnd_be: the per-proof scalar the reference draws from OsRng inside kzg::batch_verify_multi_points
  * (verifier/src/plonk/kzg.rs:149-154).
- *   NULL (the production path): the library draws n fresh 32-byte scalars from the operating system's CSPRNG
- *     (getrandom(2)) for every call, redrawing any that is 0 mod r, exactly where the reference calls Fr::random.
+ *   NULL (the production path): for every call the library draws a fresh 32-byte seed from the operating system's
+ *     CSPRNG (getrandom(2)) and expands it with ChaCha20 into n 32-byte scalars, redrawing any that is 0 mod r,
+ *     exactly where the reference calls Fr::random(OsRng).
  *   non-NULL (tests / reproducible runs only): n * 32 bytes, reduced mod r on device.  SECURITY: the scalar separates
  *     the two openings of the batched KZG check; if it is 0 mod r, or known to the prover before the proof is fixed
  *     (a constant, a reused array, a seeded PRNG), the z-shifted opening Z(omega zeta) = zu is effectively unchecked
