@@ -39,6 +39,27 @@ def test_montgomery_mul_both_fields(hs):
             assert _val(out) == a * b * rinv % mod
 
 
+def test_divsteps_inversion_equals_fermat_and_python(hs):
+    """fe_inv (Bernstein-Yang divsteps, 20 x 30) against the Fermat chain and against Python's pow, both fields: random
+    values, small and near-modulus values, sparse limbs, powers of two, zero."""
+    rng = np.random.default_rng(2)
+    for which, mod in ((0, bo.P), (1, bo.R)):
+        R = (1 << 256) % mod
+        vals = [0, 1, 2, 3, mod - 1, mod - 2, (mod - 1) // 2, (mod + 1) // 2, 1 << 30, (1 << 30) - 1, 1 << 60, 1 << 240,
+                (1 << 253) % mod, (1 << 255) % mod, mod >> 1, 0x3fffffff << 30, int("55" * 31, 16) % mod, int("aa" * 31, 16) % mod]
+        vals += [pow(2, k, mod) for k in range(0, 256, 17)] + [mod - pow(2, k, mod) for k in range(1, 256, 23)]
+        vals += [int.from_bytes(rng.bytes(32), "big") % mod for _ in range(400)]
+        vals += [int.from_bytes(rng.bytes(4), "big") for _ in range(20)]
+        vals += [(int.from_bytes(rng.bytes(32), "big") & ~((1 << 120) - 1 << 60)) % mod for _ in range(20)]  # a hole of zero bits
+        for a in vals:
+            am = a * R % mod  # Montgomery form
+            o1, o2 = (ctypes.c_uint32 * 8)(), (ctypes.c_uint32 * 8)()
+            hs.hs_fe_inv(which, _limbs(am), o1, o2)
+            want = pow(a, -1, mod) * R % mod if a else 0
+            assert _val(o1) == want, (which, hex(a))
+            assert _val(o2) == want, (which, hex(a))
+
+
 def test_fp2_mul_sqr_lazy_reduction_edge_cases(hs):
     """The lazy-reduction Fp2 multiplier (3 wide products + 2 wide reductions) on random and extreme operands."""
     import random
