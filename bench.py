@@ -294,7 +294,7 @@ def bench_groth16(ctx, pkg, peak, work):
         sampler.start()
     launches0 = pkg.launch_count()
     t0 = time.perf_counter()
-    kernel_ms, split_ms = timed_device_loop(ctx, batch, args.steps, 0, pkg.last_kernel_split)
+    kernel_ms, split_ms = timed_device_loop(ctx, batch, args.steps, 0, pkg.last_stage_ms)
     wall_kernel = time.perf_counter() - t0
     launches = pkg.launch_count() - launches0
     clocks = sampler.stop() if ctx.rank == 0 else None
@@ -316,22 +316,29 @@ def bench_groth16(ctx, pkg, peak, work):
 
     macs_per_proof = work["groth16_macs"]
     step_achieved = macs_per_proof * n * args.steps / (sum(kernel_ms) * 1e-3)
-    miller_ms = sum(a for a, b in split_ms)
-    finish_ms = sum(b for a, b in split_ms)
-    two = finish_ms > 0
-    dom_macs = work["groth16_miller_macs"] if two else macs_per_proof
+    # stages of a step (CUDA events inside the library): [prepare + Miller, final exponentiation, prepare alone]
+    front_ms = sum(s[0] for s in split_ms)
+    finish_ms = sum(s[1] for s in split_ms)
+    prepare_ms = sum(s[2] for s in split_ms if len(s) > 2)
+    multi = finish_ms > 0
+    miller_ms = front_ms - prepare_ms
+    dom_macs = (work["groth16_miller_macs"] - (work.get("groth16_prepare_macs", 0) if prepare_ms > 0 else 0)) if multi \
+        else macs_per_proof
     achieved = dom_macs * n * args.steps / (miller_ms * 1e-3)
     pk = peak["wide_mac_per_s"]
     roofline = {
         "bound": "int32-imad", "achieved": achieved / 1e12, "peak": pk / 1e12, "unit": "TMAC/s", "frac": achieved / pk,
         "traffic": ncu_traffic("k_groth16_miller", n),
-        "kernel": "k_groth16_miller" if two else "k_groth16_verify",
+        "kernel": "k_groth16_miller" if multi else "k_groth16_verify",
         "kernel_ms_per_launch": miller_ms / args.steps, "macs_per_launch": dom_macs * n,
         "share_of_step": miller_ms / sum(kernel_ms),
         "step": {"achieved": step_achieved / 1e12, "frac": step_achieved / pk,
-                 "kernels": ["k_groth16_miller", "k_groth16_finish"] if two else ["k_groth16_verify"],
+                 "kernels": ["k_groth16_prepare", "k_groth16_miller", "k_groth16_finish"] if multi else ["k_groth16_verify"],
+                 "prepare_ms_per_launch": prepare_ms / args.steps,
+                 "prepare_frac": (work.get("groth16_prepare_macs", 0) * n * args.steps / (prepare_ms * 1e-3) / pk)
+                 if prepare_ms > 0 else None,
                  "finish_ms_per_launch": finish_ms / args.steps,
-                 "finish_frac": (work["groth16_finish_macs"] * n * args.steps / (finish_ms * 1e-3) / pk) if two else None},
+                 "finish_frac": (work["groth16_finish_macs"] * n * args.steps / (finish_ms * 1e-3) / pk) if multi else None},
         "macs_per_proof": macs_per_proof, "fp_mul_per_proof": work["groth16_fp_mul"],
         "peak_source": "measured live: bn254v_imad_peak (independent IMAD.WIDE.U32 accumulate chains, 8 warps/SMSP, "
                        "all SMs); MEASURED_PEAKS.json holds no integer peak",

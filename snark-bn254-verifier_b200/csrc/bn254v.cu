@@ -1317,7 +1317,8 @@ static int batch_run(const bn254v_vk* vk, bn254v_batch* b, uint8_t* status, floa
     if (m && b->kind == 0) {
       bool two = false;
       launch::Groth16Args a{(const Groth16VkDev*)vk->dev[d], p.proofs, 256, nullptr, p.inputs, b->n_inputs, m, p.status,
-                            nullptr, nullptr, nullptr, p.fbuf, dev.ev[1]};
+                            nullptr, nullptr, nullptr, p.fbuf, dev.ev[1], dev.ev[3]};
+      CU(cudaEventRecord(dev.ev[3], dev.stream));  // (stays at the start when there is no separate prepare launch)
       g_launches += launch::groth16_verify(dev.stream, a, g_sm_count, &two);
       if (!two) CU(cudaEventRecord(dev.ev[1], dev.stream));
       CU(cudaEventRecord(dev.ev[2], dev.stream));
@@ -1345,6 +1346,10 @@ static int batch_run(const bn254v_vk* vk, bn254v_batch* b, uint8_t* status, floa
     if (d == 0 && b->parts[0].hi > b->parts[0].lo) {
       g_stage_n = n_stage;
       for (int s = 0; s < n_stage; s++) CU(cudaEventElapsedTime(&g_stage_ms[s], dev.ev[s], dev.ev[s + 1]));
+      if (b->kind == 0) {  // Groth16: [0] prepare + Miller, [1] final exponentiation, [2] the prepare launch alone
+        CU(cudaEventElapsedTime(&g_stage_ms[2], dev.ev[0], dev.ev[3]));
+        g_stage_n = 3;
+      }
       // PlonK batches above 2^16 proofs run in chunks: the split is that of the first chunk, scaled to the whole time
       if (b->kind == 1 && b->parts[0].hi - b->parts[0].lo > (1u << 16)) {
         float sum = 0.f;

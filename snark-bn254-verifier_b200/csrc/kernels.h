@@ -33,8 +33,9 @@ struct Groth16Args {
   size_t m;
   uint8_t* status;
   uint8_t *dbg_l, *dbg_m, *dbg_gt;  // or null
-  Fp12* fbuf;                       // m Miller values (two-launch shapes), or null
-  cudaEvent_t mid;                  // recorded between the two launches when non-null
+  Fp12* fbuf;                       // m Miller values (multi-launch shapes), or null
+  cudaEvent_t mid;                  // recorded between the Miller and the final-exponentiation launch when non-null
+  cudaEvent_t pre = nullptr;        // recorded after the prepare launch when non-null
 };
 int groth16_verify(cudaStream_t st, const Groth16Args& a, int sm_count, bool* two_launch);
 

@@ -109,6 +109,18 @@ void hs_groth16_vk_free(void* vk) {
   delete[] ((Groth16VkDev*)vk)->ic_table;
   delete (Groth16VkDev*)vk;
 }
+// multiply-adds of the part of a proof that k_groth16_prepare runs (decode, validation, prepare_inputs)
+unsigned long long hs_groth16_prepare_macs(void* vk, const uint8_t* proof, uint32_t proof_len, const uint8_t* inputs, int n_inputs) {
+#ifdef BN254_COUNT_MULS
+  const unsigned long long before = fe_mac_counter();
+  G1Aff A, C, L;
+  G2Aff B;
+  groth16_parse_one(A, B, C, L, *(Groth16VkDev*)vk, proof, proof_len, inputs, n_inputs);
+  return fe_mac_counter() - before;
+#else
+  return 0;
+#endif
+}
 void hs_groth16_vk_target(void* vk, uint8_t* out) { fp12_to_bytes(out, ((Groth16VkDev*)vk)->target); }
 
 int hs_groth16_verify(void* vk, const uint8_t* proof, uint32_t proof_len, const uint8_t* inputs, int n_inputs,

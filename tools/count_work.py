@@ -50,6 +50,14 @@ def main(write=True):
     hs.hs_final_exp_only(bytes.fromhex(c["miller"]))
     out["groth16_finish_macs"] = hs.hs_mul_count(1)
     out["groth16_miller_macs"] = out["groth16_macs"] - out["groth16_finish_macs"]
+    # ... of which k_groth16_prepare (decode, validation, prepare_inputs)
+    hs.hs_groth16_prepare_macs.restype = ctypes.c_ulonglong
+    hs.hs_groth16_prepare_macs.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_int]
+    tot = 0
+    for pr in case["proofs"]:
+        inputs = b"".join(int(x).to_bytes(32, "big") for x in pr["inputs"])
+        tot += hs.hs_groth16_prepare_macs(h, bytes.fromhex(pr["proof"]), 256, inputs, 2)
+    out["groth16_prepare_macs"] = tot // n
     # opt-in aggregate check (csrc/groth16_agg.cuh): one proof's share = [r] C | validation, [r] A, single-pair Miller loop
     hs.hs_groth16_agg_proof_macs.restype = ctypes.c_ulonglong
     hs.hs_groth16_agg_proof_macs.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_int,

@@ -7,4 +7,4 @@ for l in altlibs/*.so snark-bn254-verifier_b200/libbn254v.so; do
   BN254V_LIB=$PWD/$l BN254V_NVCC_EXTRA="$extra" timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-secondary "$@" 2>/dev/null | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); r=d['roofline']
-print('step ms', d['ms_per_step'], 'proofs/s', d['value'], 'miller', r['kernel_ms_per_launch'], 'finish', r['step']['finish_ms_per_launch'], 'frac', r['frac'])"; done
+print('step ms', d['ms_per_step'], 'proofs/s', d['value'], 'miller', r['kernel_ms_per_launch'], 'prepare', r['step']['prepare_ms_per_launch'], 'finish', r['step']['finish_ms_per_launch'], 'frac', r['frac'])"; done
