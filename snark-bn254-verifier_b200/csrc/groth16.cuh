@@ -93,9 +93,10 @@ struct Groth16Debug {
 };
 
 // proof: >= 256 bytes (A | B | C), proof_len: valid bytes.
-// The verification in two halves, so that the batch kernels can run them as two launches (each with half the code
-// and half the stack): (1) decode, validate, prepare_inputs, Miller loop -> the Fq12 Miller value;
-// (2) final exponentiation and comparison with e(alpha, beta').
+// The verification in pieces, so that the batch kernels can run them as separate launches (each with a fraction of the
+// code and stack): groth16_parse_one (decode, validate, prepare_inputs), the Miller loop -> the Fq12 Miller value
+// (groth16_miller_one = both, for the fused small-batch kernel), groth16_finish_one (final exponentiation and
+// comparison with e(alpha, beta')).
 // Barrier discipline: miller_loop_pairtab / final_exponentiation contain block-wide phase barriers, so every thread of a
 // block must reach them the same number of times.  A proof that fails before the Miller loop is therefore NOT ended
 // early: its status is recorded and the thread runs the loop on substitute VK points (always valid, order r), whose
