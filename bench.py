@@ -398,7 +398,7 @@ def bench_all_valid(ctx, pkg, peak, work):
                        "proofs_per_gpu": n},
             "e2e": {"value": world * n * args.steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": vp.nbytes + vi.nbytes + 16 * n, "d2h_bytes_per_step": n + 1},
-            "roofline": {"bound": "int32-imad", "kernel": "k_groth16_agg_c + k_groth16_agg_miller (+ product tree)",
+            "roofline": {"bound": "int32-imad", "kernel": "k_groth16_agg_prepare + k_groth16_agg_miller (+ product tree)",
                          "achieved": achieved / 1e12 if achieved else None, "peak": pk / 1e12, "unit": "TMAC/s",
                          "frac": achieved / pk if achieved else None, "traffic": ncu_traffic("k_groth16_agg_miller", n),
                          "macs_per_proof": macs,

@@ -830,7 +830,7 @@ static int groth16_batch_all_valid_impl(const bn254v_vk* vk, const uint8_t* proo
                                  p.rnd.as<uint8_t>(), m, p.status.as<uint8_t>(), p.fbuf.as<Fp12>(), p.gbuf.as<G1Jac>(),
                                  p.scal.as<uint8_t>(), p.scratch.p, p.verdict.as<uint8_t>()};
     if (d == 0) CU(cudaEventRecord(dev.ev[0], dev.stream));
-    g_launches += launch::groth16_agg_c(dev.stream, p.a);
+    g_launches += launch::groth16_agg_prepare(dev.stream, p.a);
     CU(cudaEventRecord(dev.side_ev[0], dev.stream));
     g_launches += launch::groth16_agg_miller(dev.stream, p.a, g_sm_count, &p.product);
     CU(cudaGetLastError());

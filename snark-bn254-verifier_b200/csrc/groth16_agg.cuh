@@ -72,34 +72,30 @@ HD int groth16_agg_parse_one(G1Aff& A, G2Aff& B, G1Aff& C, const Groth16VkDev& v
   return st;
 }
 
-// One proof's shares.  (1) rc = [r_i] C_i -- or O when the record is short or C is not a curve point (the proof then
-// fails validation in (2) anyway).  Separate from (2) so that the batch's own pairing, which needs sum rc, can run
-// while the Miller loops of the proofs are still going.
-HD G1Jac groth16_agg_c_one(const uint8_t* proof, uint32_t proof_len, const uint8_t* rnd16) {
-  G1Aff C;
-  if (proof_len < 256 || load_g1_checked(C, proof + 192) != BN254V_OK_TRUE) return jac_identity<Fp>();
-  uint32_t a[2], b[2];
-  groth16_agg_scalar(a, b, rnd16);
-  return g1_mul_glv64(C, a, b);
-}
-// (2) f = ML(r_i A_i, B_i).  A proof that fails validation (or a spare thread, `live == false`) contributes f = 1 and
-// walks the loop on substitute VK points (block-wide barriers inside).
-HD int groth16_agg_one(Fp12& f, const Groth16VkDev& vk, const uint8_t* proof, uint32_t proof_len,
-                       const uint8_t* inputs_be, int n_inputs, const uint8_t* rnd16, bool live = true) {
+// One proof's shares.  (1) Everything before its Miller loop (k_groth16_agg_prepare: one thread per proof in small
+// blocks, no barriers): validation, rA = [r_i] A_i in affine coordinates, rc = [r_i] C_i.  A proof that fails validation
+// contributes rc = O.  First and on its own so that the batch's own pairing, which needs sum rc, can run while the
+// Miller loops of the proofs are still going.
+HD int groth16_agg_prepare_one(G1Aff& rA, G2Aff& B, G1Jac& rc, const Groth16VkDev& vk, const uint8_t* proof,
+                               uint32_t proof_len, const uint8_t* inputs_be, int n_inputs, const uint8_t* rnd16) {
   G1Aff A, C;
-  G2Aff B;
-  int st = groth16_agg_parse_one(A, B, C, vk, proof, proof_len, inputs_be, n_inputs, live);
-  const bool ok = st == BN254V_OK_TRUE;
-  if (!ok) A = vk.alpha, B = vk.beta;
+  const int st = groth16_agg_parse_one(A, B, C, vk, proof, proof_len, inputs_be, n_inputs, true);
+  rc = jac_identity<Fp>();
+  if (st != BN254V_OK_TRUE) return st;
   uint32_t a[2], b[2];
   groth16_agg_scalar(a, b, rnd16);
-  G1Aff rA;
+  rc = g1_mul_glv64(C, a, b);
   to_affine(rA, g1_mul_glv64(A, a, b));  // A has order r and r_i != 0: never the identity
+  return st;
+}
+// (2) f = ML(r_i A_i, B_i) and B's membership in G2, read off the end point of the loop.  `ok == false` (the proof failed
+// validation, or a spare thread of the last block): the loop runs on substitute VK points for its block-wide barriers.
+HD bool groth16_agg_miller_one(Fp12& f, const Groth16VkDev& vk, G1Aff rA, G2Aff B, bool ok) {
+  if (!ok) rA = vk.alpha, B = vk.beta;
   bool in_g2;
   miller_loop<1, 0>(f, &rA, &B, nullptr, nullptr, 0, &in_g2);
-  if (ok && !in_g2) st = BN254V_PANIC_NOT_IN_SUBGROUP;
-  if (st != BN254V_OK_TRUE) f = fp12_one();
-  return st;
+  if (!ok || !in_g2) f = fp12_one();
+  return in_g2;
 }
 
 // The batch's own three pairs: (-(s) alpha, beta'), (s IC_0 + sum t_j IC_j, gamma'), (sum r_i C_i, delta').

@@ -1,11 +1,11 @@
 // Kernels of the opt-in aggregate Groth16 check (groth16_agg.cuh).  sm_100a only.
-//   main stream   k_groth16_agg_c       one proof per thread: [r_i] C_i
-//                 k_groth16_agg_miller  one proof per thread: validate, [r_i] A_i, the single-pair Miller loop of (r_i A_i, B_i)
+//   main stream   k_groth16_agg_prepare one proof per thread, small blocks: validate, [r_i] A_i (affine), [r_i] C_i
+//                 k_groth16_agg_miller  one proof per thread: the single-pair Miller loop of (r_i A_i, B_i), B in G2
 //                 k_groth16_agg_fold_f  product tree over the Miller values
 //                 k_groth16_agg_final3  three lanes (trio.cuh): F * f', final exponentiation, == 1
 //   side stream   k_groth16_agg_fold_g  sum tree over the [r_i] C_i                             } a handful of threads,
-//   (after _c)    k_groth16_agg_points  the batch's three G1 points from the host's scalar sums  } underneath the
-//                 k_groth16_agg_fprime3 three lanes: the batch's own three-pair Miller loop f'   } proofs' Miller loops
+//   (after        k_groth16_agg_points  the batch's three G1 points from the host's scalar sums  } underneath the
+//    _prepare)    k_groth16_agg_fprime3 three lanes: the batch's own three-pair Miller loop f'   } proofs' Miller loops
 // Same barrier discipline as k_groth16.cu: nothing returns before the last block-wide barrier.
 #include "kernels.h"
 #include "groth16_agg.cuh"
@@ -14,32 +14,43 @@
 namespace bn254 {
 namespace {
 
-__global__ void __launch_bounds__(128)
-    k_groth16_agg_c(const uint8_t* __restrict__ proofs, size_t stride, const uint32_t* __restrict__ proof_len,
-                    const uint8_t* __restrict__ rnd16, size_t n, G1Jac* __restrict__ gbuf) {
+__global__ void __launch_bounds__(64, 4)
+    k_groth16_agg_prepare(const Groth16VkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride,
+                          const uint32_t* __restrict__ proof_len, const uint8_t* __restrict__ inputs, int n_inputs,
+                          const uint8_t* __restrict__ rnd16, size_t n, uint8_t* __restrict__ status,
+                          Fp12* __restrict__ fbuf, G1Jac* __restrict__ gbuf) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;  // (no barriers in this kernel)
   uint32_t len = proof_len ? proof_len[i] : (uint32_t)stride;
   if (len > stride) len = (uint32_t)stride;
-  gbuf[i] = groth16_agg_c_one(proofs + stride * i, len, rnd16 + 16 * i);
+  G1Aff rA;
+  G2Aff B;
+  G1Jac rc;
+  const int st = groth16_agg_prepare_one(rA, B, rc, *vk, proofs + stride * i, len, inputs + (size_t)32 * n_inputs * i,
+                                         n_inputs, rnd16 + 16 * i);
+  status[i] = (uint8_t)st;
+  gbuf[i] = rc;
+  if (st == BN254V_OK_TRUE) *(G1Aff*)&fbuf[i] = rA;  // parked for k_groth16_agg_miller
 }
 
 template <int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB)
-    k_groth16_agg_miller(const Groth16VkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride,
-                         const uint32_t* __restrict__ proof_len, const uint8_t* __restrict__ inputs, int n_inputs,
-                         const uint8_t* __restrict__ rnd16, size_t n, uint8_t* __restrict__ status,
-                         Fp12* __restrict__ fbuf) {
+    k_groth16_agg_miller(const Groth16VkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride, size_t n,
+                         uint8_t* __restrict__ status, Fp12* __restrict__ fbuf) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < n;
-  if (!live) i = n - 1;  // spare threads of the last block walk the last proof and write nothing
-  uint32_t len = proof_len ? proof_len[i] : (uint32_t)stride;
-  if (len > stride) len = (uint32_t)stride;
+  if (!live) i = n - 1;  // spare threads of the last block walk substitutes and write nothing
+  const bool ok = live && status[i] == BN254V_OK_TRUE;
+  G1Aff rA = vk->alpha;
+  G2Aff B = vk->beta;
+  if (ok) {
+    rA = *(const G1Aff*)&fbuf[i];
+    load_g2_unchecked(B, proofs + stride * i + 64);  // validated by k_groth16_agg_prepare
+  }
   Fp12 f;
-  const int st = groth16_agg_one(f, *vk, proofs + stride * i, len, inputs + (size_t)32 * n_inputs * i, n_inputs,
-                                 rnd16 + 16 * i, live);
+  const bool in_g2 = groth16_agg_miller_one(f, *vk, rA, B, ok);
   if (!live) return;
-  status[i] = (uint8_t)st;
+  if (ok && !in_g2) status[i] = BN254V_PANIC_NOT_IN_SUBGROUP;
   fbuf[i] = f;
 }
 
@@ -123,13 +134,14 @@ namespace launch {
 size_t groth16_agg_scratch_bytes() { return sizeof(AggScratch); }
 size_t groth16_agg_slots(size_t m) { return m + (m + 3) / 4; }
 
-// main stream, first: the [r_i] C_i
-int groth16_agg_c(cudaStream_t st, const Groth16AggArgs& a) {
-  k_groth16_agg_c<<<(unsigned)((a.m + 127) / 128), 128, 0, st>>>(a.proofs, a.stride, a.lens, a.rnd16, a.m, a.gbuf);
+// main stream, first: validation, [r_i] A_i, [r_i] C_i
+int groth16_agg_prepare(cudaStream_t st, const Groth16AggArgs& a) {
+  k_groth16_agg_prepare<<<(unsigned)((a.m + 63) / 64), 64, 0, st>>>(a.vk, a.proofs, a.stride, a.lens, a.inputs, a.n_inputs,
+                                                                   a.rnd16, a.m, a.status, a.fbuf, a.gbuf);
   return 1;
 }
 
-// side stream, once groth16_agg_c is done and a.scal_be is on the device: sum tree, points, the batch's Miller value
+// side stream, once groth16_agg_prepare is done and a.scal_be is on the device: sum tree, points, the batch's Miller value
 int groth16_agg_side(cudaStream_t st, const Groth16AggArgs& a) {
   int launches = 0;
   const G1Jac* sum = fold_passes(st, a.gbuf, a.m, k_groth16_agg_fold_g, &launches);
@@ -144,8 +156,7 @@ int groth16_agg_miller(cudaStream_t st, const Groth16AggArgs& a, int sm_count, F
   const size_t m = a.m;
   const int shape = pick_shape(m, sm_count);
 #define LA(TPB, MINB)                                                                                                     \
-  k_groth16_agg_miller<TPB, MINB><<<(unsigned)((m + TPB - 1) / TPB), TPB, 0, st>>>(a.vk, a.proofs, a.stride, a.lens, a.inputs, \
-                                                                                   a.n_inputs, a.rnd16, m, a.status, a.fbuf)
+  k_groth16_agg_miller<TPB, MINB><<<(unsigned)((m + TPB - 1) / TPB), TPB, 0, st>>>(a.vk, a.proofs, a.stride, m, a.status, a.fbuf)
   switch (shape) {
     case SHAPE_448: LA(448, 1); break;
     case SHAPE_384: LA(384, 1); break;

@@ -58,9 +58,9 @@ struct Groth16AggArgs {
 };
 size_t groth16_agg_scratch_bytes();
 size_t groth16_agg_slots(size_t m);
-// main stream: _c, then _miller (-> where the product of the Miller values lands), then -- after the side stream --
-// _final; side stream, after _c: _side (sum tree, the batch's points and its own Miller value)
-int groth16_agg_c(cudaStream_t st, const Groth16AggArgs& a);
+// main stream: _prepare, then _miller (-> where the product of the Miller values lands), then -- after the side stream --
+// _final; side stream, after _prepare: _side (sum tree, the batch's points and its own Miller value)
+int groth16_agg_prepare(cudaStream_t st, const Groth16AggArgs& a);
 int groth16_agg_side(cudaStream_t st, const Groth16AggArgs& a);
 int groth16_agg_miller(cudaStream_t st, const Groth16AggArgs& a, int sm_count, Fp12** product);
 int groth16_agg_final(cudaStream_t st, const Groth16AggArgs& a, const Fp12* product);

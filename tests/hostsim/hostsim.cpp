@@ -458,15 +458,17 @@ void hs_groth16_vk_add_agg_tables(void* vkp) {
 }
 // multiply-adds of one proof's share of the aggregate check: [r] C, then validation + [r] A + the single-pair Miller loop
 unsigned long long hs_groth16_agg_proof_macs(void* vkp, const uint8_t* proof, uint32_t len, const uint8_t* inputs, int n_inputs,
-                                             const uint8_t* rnd16, unsigned long long* c_part) {
+                                             const uint8_t* rnd16, unsigned long long* prepare_part) {
 #ifdef BN254_COUNT_MULS
   const unsigned long long before = fe_mac_counter();
-  G1Jac g = groth16_agg_c_one(proof, len, rnd16);
+  G1Aff rA;
+  G2Aff B;
+  G1Jac g;
+  const int st = groth16_agg_prepare_one(rA, B, g, *(Groth16VkDev*)vkp, proof, len, inputs, n_inputs, rnd16);
   const unsigned long long mid = fe_mac_counter();
   Fp12 f;
-  groth16_agg_one(f, *(Groth16VkDev*)vkp, proof, len, inputs, n_inputs, rnd16);
-  (void)g;
-  if (c_part) *c_part = mid - before;
+  groth16_agg_miller_one(f, *(Groth16VkDev*)vkp, rA, B, st == BN254V_OK_TRUE);
+  if (prepare_part) *prepare_part = mid - before;
   return fe_mac_counter() - before;
 #else
   return 0;
@@ -483,8 +485,11 @@ int hs_groth16_agg(void* vkp, const uint8_t* proofs, size_t stride, const uint32
   bool all_ok = true;
   for (int i = 0; i < n; i++) {
     const uint32_t len = lens ? lens[i] : (uint32_t)stride;
-    g[i] = groth16_agg_c_one(proofs + stride * i, len, rnd16 + 16 * i);
-    int st = groth16_agg_one(f[i], vk, proofs + stride * i, len, inputs + (size_t)32 * n_inputs * i, n_inputs, rnd16 + 16 * i);
+    G1Aff rA;
+    G2Aff B;
+    int st = groth16_agg_prepare_one(rA, B, g[i], vk, proofs + stride * i, len, inputs + (size_t)32 * n_inputs * i, n_inputs,
+                                     rnd16 + 16 * i);
+    if (!groth16_agg_miller_one(f[i], vk, rA, B, st == BN254V_OK_TRUE) && st == BN254V_OK_TRUE) st = BN254V_PANIC_NOT_IN_SUBGROUP;
     status_out[i] = (uint8_t)st;
     if (st != BN254V_OK_TRUE) all_ok = false;
     if (f_out) fp12_to_bytes(f_out + 384 * (size_t)i, f[i]);

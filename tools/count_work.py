@@ -58,7 +58,7 @@ def main(write=True):
         inputs = b"".join(int(x).to_bytes(32, "big") for x in pr["inputs"])
         tot += hs.hs_groth16_prepare_macs(h, bytes.fromhex(pr["proof"]), 256, inputs, 2)
     out["groth16_prepare_macs"] = tot // n
-    # opt-in aggregate check (csrc/groth16_agg.cuh): one proof's share = [r] C | validation, [r] A, single-pair Miller loop
+    # opt-in aggregate check (csrc/groth16_agg.cuh): one proof's share = validation, [r] A, [r] C | single-pair Miller loop
     hs.hs_groth16_agg_proof_macs.restype = ctypes.c_ulonglong
     hs.hs_groth16_agg_proof_macs.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_int,
                                              ctypes.c_char_p, ctypes.POINTER(ctypes.c_ulonglong)]
@@ -70,7 +70,7 @@ def main(write=True):
         tot += hs.hs_groth16_agg_proof_macs(h, bytes.fromhex(pr["proof"]), 256, inputs, 2, rnd, ctypes.byref(cp))
         cpart += cp.value
     out["groth16_agg_macs"] = tot // n
-    out["groth16_agg_c_macs"] = cpart // n
+    out["groth16_agg_prepare_macs"] = cpart // n
     # raw pairing products
     for c in load_json("pairing_golden.json"):
         if c["is_one"]:
