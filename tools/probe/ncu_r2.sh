@@ -18,10 +18,16 @@ cap() {  # name, kernel regex, skip, command...
   ncu -i gpurun_out/$name.ncu-rep --page source --csv > gpurun_out/r2_${name}_src.csv 2>/dev/null
   rm -f gpurun_out/$name.ncu-rep
 }
+cap prepare k_groth16_prepare 3 $G
 cap miller k_groth16_miller 3 $G
 cap finish k_groth16_finish 3 $G
 cap terms k_plonk_terms 2 $P16
 cap stage_e k_plonk_stage_e 1 $P16
 cap stage_e3 k_plonk_stage_e3 1 $P14
 cap pairing k_pairing_product 1 $Q
+A="python tools/probe/agg_only.py 16 2"
+timeout 300 $A > gpurun_out/r2_plain_agg.log 2>&1 || exit 1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_groth16_agg -c 80 --csv --log-file gpurun_out/r2_agg_launches.csv $A > gpurun_out/r2_ncu_agg_l.log 2>&1
+cap agg_miller k_groth16_agg_miller 1 $A
+cap agg_prepare k_groth16_agg_prepare 1 $A
 ls -la gpurun_out | tail -20
