@@ -20,23 +20,28 @@
 // prepare_inputs (it needs a discrete-log relation between the IC points of the VK).
 #pragma once
 #include "groth16.cuh"
-#include "plonk.cuh"  // g1_w4_table / g1_w4_add_digits / g1_mul_fixed
+#include "plonk.cuh"  // g1_w4_tables / g1_w4_add_digits / g1_mul_fixed
 
 namespace bn254 {
 
-// [a + b lambda] P, a and b 64-bit (2 LE words each)
-HDN G1Jac g1_mul_glv64(const G1Aff& p, const uint32_t* a, const uint32_t* b) {
+// [a + b lambda] P_0 and [a + b lambda] P_1, a and b 64-bit (2 LE words each): signed 4-bit windows over two 8-entry
+// affine tables that share one inversion (plonk.cuh g1_w4_tables); 17 windows, 64 doublings per point.
+HDN void g1_mul_glv64_2(G1Jac* out, const G1Aff* p, const uint32_t* a, const uint32_t* b) {
   Fp beta;
   BN_LOAD_FP(beta, K::glv_beta, 0);
-  G1Jac tab[15];
-  g1_w4_table(tab, p);
-  G1Jac acc = jac_identity<Fp>();
-  for (int w = 15; w >= 0; w--) {
-    if (w != 15)
-      for (int j = 0; j < 4; j++) acc = jac_double(acc);
-    g1_w4_add_digits(acc, tab, a, b, false, false, beta, w);
+  uint32_t ka[5] = {a[0], a[1], 0, 0, 0}, kb[5] = {b[0], b[1], 0, 0, 0};
+  w4_offset(ka), w4_offset(kb);  // the windows above the 17th hold the digit 0
+  G1Aff tab[16];
+  g1_w4_tables(tab, p, 2);
+  for (int v = 0; v < 2; v++) {
+    G1Jac acc = jac_identity<Fp>();
+    for (int w = 16; w >= 0; w--) {
+      if (w != 16)
+        for (int j = 0; j < 4; j++) acc = jac_double(acc);
+      g1_w4_add_digits(acc, tab + 8 * v, ka, kb, false, false, beta, w);
+    }
+    out[v] = acc;
   }
-  return acc;
 }
 
 // the scalar halves of proof i: 16 bytes = a (LE u64) | b (LE u64); a is made odd, so r_i != 0
@@ -84,8 +89,11 @@ HD int groth16_agg_prepare_one(G1Aff& rA, G2Aff& B, G1Jac& rc, const Groth16VkDe
   if (st != BN254V_OK_TRUE) return st;
   uint32_t a[2], b[2];
   groth16_agg_scalar(a, b, rnd16);
-  rc = g1_mul_glv64(C, a, b);
-  to_affine(rA, g1_mul_glv64(A, a, b));  // A has order r and r_i != 0: never the identity
+  const G1Aff pts[2] = {A, C};
+  G1Jac res[2];
+  g1_mul_glv64_2(res, pts, a, b);
+  rc = res[1];
+  to_affine(rA, res[0]);  // A has order r and r_i != 0: never the identity
   return st;
 }
 // (2) f = ML(r_i A_i, B_i) and B's membership in G2, read off the end point of the loop.  `ok == false` (the proof failed

@@ -47,7 +47,10 @@ __global__ void __launch_bounds__(64)
   }
 }
 
-__global__ void __launch_bounds__(64)
+#ifndef BN_TERMS_MINB
+#define BN_TERMS_MINB 8  // blocks of 64 threads per SM: <= 128 registers, 4 warps per sub-partition
+#endif
+__global__ void __launch_bounds__(64, BN_TERMS_MINB)
     k_plonk_terms(const PlonkVkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride, PlonkWork* work,
                   const int* __restrict__ list, const int* __restrict__ count, int stage, int joint) {
   int slot = blockIdx.x * blockDim.x + threadIdx.x;

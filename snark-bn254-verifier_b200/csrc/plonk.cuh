@@ -140,9 +140,9 @@ HD bool glv_abs(uint32_t* v) {  // two's complement -> magnitude; returns the si
   uint32_t name[8];                     \
   _Pragma("unroll") for (int _i = 0; _i < 8; _i++) name[_i] = fn(_i);
 
-// [k] P for a proof-supplied point: GLV split, then fixed 4-bit windows for both halves over one 15-entry table
-// (phi of a table entry is one multiplication by beta) with shared doublings: 132 doublings + at most 66 additions
-// instead of 252 + 64; uniform control flow across a warp apart from zero digits.  k: plain 8 x u32 LE (< r).
+// [k] P for a proof-supplied point: GLV split, then SIGNED 4-bit windows for both halves over one 8-entry AFFINE
+// table (phi of a table entry is one multiplication by beta) with shared doublings: 132 doublings + at most 66 mixed
+// additions instead of 252 + 64; uniform control flow across a warp apart from zero digits.  k: plain 8 x u32 LE (< r).
 // Same group element as the reference's AffineG1 * Fr; AffineG1::msm is a plain sum of such terms.
 // k -> (|k1|, |k2|, signs)
 HD void glv_split(uint32_t* k1, uint32_t* k2, bool& n1, bool& n2, const uint32_t* k) {
@@ -166,38 +166,74 @@ HD void glv_split(uint32_t* k1, uint32_t* k2, bool& n1, bool& n2, const uint32_t
   }
   n1 = glv_abs(k1), n2 = glv_abs(k2);
 }
-// tab[d - 1] = d P, d = 1..15
-HD void g1_w4_table(G1Jac* tab, const G1Aff& p) {
-  tab[0] = to_jac(p);
-  tab[1] = jac_double(tab[0]);
-  for (int i = 2; i < 15; i++) tab[i] = jac_add_mixed(tab[i - 1], p);
+// Signed digits without carries: v + 0x888..8 (33 nibbles of 8) has nibbles n_w with sum (n_w - 8) 16^w = v, so the
+// digit of window w is n_w - 8 in [-8, 7] and can be read most significant window first.  Needs v < 7 * 2^128 (the GLV
+// halves are < 2^128: tools/gen_constants.py glv(), tests/test_hostsim.py).
+HD void w4_offset(uint32_t* v) {
+  v[0] = cc::add_cc(v[0], 0x88888888u);
+  v[1] = cc::addc_cc(v[1], 0x88888888u);
+  v[2] = cc::addc_cc(v[2], 0x88888888u);
+  v[3] = cc::addc_cc(v[3], 0x88888888u);
+  v[4] = cc::addc(v[4], 0x8u);
 }
-// acc += [digit of k1 at nibble w] P + [digit of k2 at nibble w] phi(P)
-HD void g1_w4_add_digits(G1Jac& acc, const G1Jac* tab, const uint32_t* k1, const uint32_t* k2, bool n1, bool n2,
+HD int w4_digit(const uint32_t* v, int w) { return (int)((v[w >> 3] >> (4 * (w & 7))) & 15) - 8; }
+// tab[8 j + d - 1] = d P_j, d = 1..8, in AFFINE coordinates for each of n points, with one inversion for all of them
+// (Montgomery's trick over the 7 n Jacobian z coordinates).  The points are on the curve (validated in stage A; VK
+// points by the VK loader), hence of order r: no multiple below r is the identity and no z is zero.  An affine entry
+// makes every window addition a mixed one (11 multiplications instead of 16) and takes 64 bytes instead of 96; the
+// affine coordinates of a multiple are unique, so the sums are the same group elements as with Jacobian entries.
+#define BN_MSM_MAX 3
+HD void g1_w4_tables(G1Aff* tab, const G1Aff* p, int n) {
+  Fp z[7 * BN_MSM_MAX], c[7 * BN_MSM_MAX];
+  Fp run = fe_one<FpCfg>();
+  for (int j = 0; j < n; j++) {
+    tab[8 * j] = p[j];
+    G1Jac a = jac_double(to_jac(p[j]));
+    for (int d = 0; d < 7; d++) {
+      if (d) a = jac_add_mixed(a, p[j]);
+      tab[8 * j + 1 + d] = G1Aff{a.x, a.y};  // Jacobian X, Y until the pass below
+      z[7 * j + d] = a.z;
+      c[7 * j + d] = run;  // product of all earlier z
+      run = fe_mul(run, a.z);
+    }
+  }
+  Fp iv = fe_inv(run);
+  for (int i = 7 * n - 1; i >= 0; i--) {
+    const Fp zi = fe_mul(iv, c[i]);
+    iv = fe_mul(iv, z[i]);
+    const Fp zi2 = fe_sqr(zi);
+    G1Aff& e = tab[8 * (i / 7) + 1 + (i % 7)];
+    e.x = fe_mul(e.x, zi2);
+    e.y = fe_mul(e.y, fe_mul(zi2, zi));
+  }
+}
+// acc += [digit of k1 at window w] P + [digit of k2 at window w] phi(P); k1, k2 offset by w4_offset
+HD void g1_w4_add_digits(G1Jac& acc, const G1Aff* tab, const uint32_t* k1, const uint32_t* k2, bool n1, bool n2,
                          const Fp& beta, int w) {
-  const uint32_t d1 = (k1[w >> 3] >> (4 * (w & 7))) & 15, d2 = (k2[w >> 3] >> (4 * (w & 7))) & 15;
+  const int d1 = w4_digit(k1, w), d2 = w4_digit(k2, w);
   if (d1) {
-    G1Jac t = tab[d1 - 1];
-    if (n1) t.y = fe_neg(t.y);
-    acc = jac_add(acc, t);
+    G1Aff t = tab[(d1 < 0 ? -d1 : d1) - 1];
+    if (n1 != (d1 < 0)) t.y = fe_neg(t.y);
+    acc = jac_add_mixed(acc, t);
   }
   if (d2) {
-    G1Jac t = tab[d2 - 1];
+    G1Aff t = tab[(d2 < 0 ? -d2 : d2) - 1];
     t.x = fe_mul(t.x, beta);
-    if (n2) t.y = fe_neg(t.y);
-    acc = jac_add(acc, t);
+    if (n2 != (d2 < 0)) t.y = fe_neg(t.y);
+    acc = jac_add_mixed(acc, t);
   }
 }
 HDN G1Jac g1_mul_w4(const G1Aff& p, const uint32_t* k) {
   uint32_t k1[8], k2[8];
   bool n1, n2;
   glv_split(k1, k2, n1, n2, k);
+  w4_offset(k1), w4_offset(k2);
   Fp beta;
   BN_LOAD_FP(beta, K::glv_beta, 0);
-  G1Jac tab[15];
-  g1_w4_table(tab, p);
+  G1Aff tab[8];
+  g1_w4_tables(tab, &p, 1);
   G1Jac acc = jac_identity<Fp>();
-  for (int w = 32; w >= 0; w--) {  // 33 nibbles = 132 bits >= |k1|, |k2|
+  for (int w = 32; w >= 0; w--) {  // 33 windows: the offset form of a 128-bit value carries into the 33rd
     if (w != 32)
       for (int j = 0; j < 4; j++) acc = jac_double(acc);
     g1_w4_add_digits(acc, tab, k1, k2, n1, n2, beta, w);
@@ -205,24 +241,24 @@ HDN G1Jac g1_mul_w4(const G1Aff& p, const uint32_t* k) {
   return acc;
 }
 // sum_j [k_j] P_j for up to BN_MSM_MAX proof-supplied points, evaluated jointly (Straus): the 132 doublings are paid once
-// for the group instead of once per point.  Same group element as the sum of the separate products (AffineG1::msm sums
-// its terms; only the total is converted to affine coordinates).
-#define BN_MSM_MAX 3
+// for the group instead of once per point, and the tables of the group share one inversion.  Same group element as the
+// sum of the separate products (AffineG1::msm sums its terms; only the total is converted to affine coordinates).
 HDN G1Jac g1_msm_w4(const G1Aff* p, const uint32_t* const* k, int n) {
   uint32_t k1[BN_MSM_MAX][8], k2[BN_MSM_MAX][8];
   bool n1[BN_MSM_MAX], n2[BN_MSM_MAX];
-  G1Jac tab[BN_MSM_MAX][15];
+  G1Aff tab[BN_MSM_MAX * 8];
   for (int j = 0; j < n; j++) {
     glv_split(k1[j], k2[j], n1[j], n2[j], k[j]);
-    g1_w4_table(tab[j], p[j]);
+    w4_offset(k1[j]), w4_offset(k2[j]);
   }
+  g1_w4_tables(tab, p, n);
   Fp beta;
   BN_LOAD_FP(beta, K::glv_beta, 0);
   G1Jac acc = jac_identity<Fp>();
   for (int w = 32; w >= 0; w--) {
     if (w != 32)
       for (int j = 0; j < 4; j++) acc = jac_double(acc);
-    for (int j = 0; j < n; j++) g1_w4_add_digits(acc, tab[j], k1[j], k2[j], n1[j], n2[j], beta, w);
+    for (int j = 0; j < n; j++) g1_w4_add_digits(acc, tab + 8 * j, k1[j], k2[j], n1[j], n2[j], beta, w);
   }
   return acc;
 }
