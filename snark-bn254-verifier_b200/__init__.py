@@ -586,32 +586,46 @@ _ITEM_DTYPE = np.dtype([("kind", "<i4"), ("n_inputs", "<i4"), ("proof", "<u8"), 
 assert _ITEM_DTYPE.itemsize == ctypes.sizeof(_Item)
 
 
+class MixedItems:
+    """The bn254v_item array of a BASELINE.json configs[4]-shaped batch: n Groth16 records and n PlonK records,
+    interleaved one to one (item 2i is Groth16 record i, item 2i + 1 is PlonK record i).  The items point into the
+    caller's arrays (no copies; the library gathers each group on the host cores inside the call).  Built once and
+    verified any number of times: a C or Rust caller holds such an array already, and filling 2n structured records
+    from numpy costs about as much as verifying them."""
+
+    def __init__(self, vk_g, proofs_g, inputs_g, vk_p, proofs_p, inputs_p, rnd_p=None):
+        proofs_g, inputs_g = np.ascontiguousarray(proofs_g, np.uint8), np.ascontiguousarray(inputs_g, np.uint8)
+        proofs_p, inputs_p = np.ascontiguousarray(proofs_p, np.uint8), np.ascontiguousarray(inputs_p, np.uint8)
+        n = proofs_g.shape[0]
+        assert proofs_p.shape[0] == n
+        vg, vp = np.frombuffer(bytes(vk_g), np.uint8), np.frombuffer(bytes(vk_p), np.uint8)
+        items = np.zeros(2 * n, dtype=_ITEM_DTYPE)
+        idx = np.arange(n, dtype=np.uint64)
+        g, p = items[0::2], items[1::2]
+        g["kind"], g["n_inputs"], g["proof_len"] = KIND_GROTH16, inputs_g.shape[1], proofs_g.shape[1]
+        g["proof"] = proofs_g.ctypes.data + idx * np.uint64(proofs_g.shape[1])
+        g["inputs"] = inputs_g.ctypes.data + idx * np.uint64(32 * inputs_g.shape[1])
+        g["vk"], g["vk_len"] = vg.ctypes.data, vg.size
+        p["kind"], p["n_inputs"], p["proof_len"] = KIND_PLONK, inputs_p.shape[1], proofs_p.shape[1]
+        p["proof"] = proofs_p.ctypes.data + idx * np.uint64(proofs_p.shape[1])
+        p["inputs"] = inputs_p.ctypes.data + idx * np.uint64(32 * inputs_p.shape[1])
+        p["vk"], p["vk_len"] = vp.ctypes.data, vp.size
+        self.rnd = None
+        if rnd_p is not None:
+            self.rnd = np.zeros((2 * n, 32), np.uint8)
+            self.rnd[1::2] = rnd_p
+        self.n_items, self.items = 2 * n, items
+        self._keep = (proofs_g, inputs_g, proofs_p, inputs_p, vg, vp)  # the items point into these
+
+    def verify(self, sign_mode=0, out=None):
+        """ONE bn254v_verify_many call over the items; returns the status bytes (written into `out` when given)."""
+        lib = load_library()
+        status = np.full(self.n_items, STATUS_UNSET, dtype=np.uint8) if out is None else out
+        _check(lib.bn254v_verify_many(ctypes.cast(self.items.ctypes.data, POINTER(_Item)), self.n_items, sign_mode,
+                                      _ptr(self.rnd), _ptr(status)))
+        return status
+
+
 def verify_mixed_arrays(vk_g, proofs_g, inputs_g, vk_p, proofs_p, inputs_p, rnd_p=None, sign_mode=0, out=None):
-    """BASELINE.json configs[4] shape: n Groth16 records and n PlonK records, interleaved one to one (item 2i is Groth16
-    record i, item 2i + 1 is PlonK record i), verified by ONE bn254v_verify_many call.  The item array points into the
-    caller's arrays (no Python loop, no copies here; the library gathers each group on the host cores)."""
-    lib = load_library()
-    proofs_g, inputs_g = np.ascontiguousarray(proofs_g, np.uint8), np.ascontiguousarray(inputs_g, np.uint8)
-    proofs_p, inputs_p = np.ascontiguousarray(proofs_p, np.uint8), np.ascontiguousarray(inputs_p, np.uint8)
-    n = proofs_g.shape[0]
-    assert proofs_p.shape[0] == n
-    vg, vp = np.frombuffer(bytes(vk_g), np.uint8), np.frombuffer(bytes(vk_p), np.uint8)
-    items = np.zeros(2 * n, dtype=_ITEM_DTYPE)
-    idx = np.arange(n, dtype=np.uint64)
-    g, p = items[0::2], items[1::2]
-    g["kind"], g["n_inputs"], g["proof_len"] = KIND_GROTH16, inputs_g.shape[1], proofs_g.shape[1]
-    g["proof"] = proofs_g.ctypes.data + idx * np.uint64(proofs_g.shape[1])
-    g["inputs"] = inputs_g.ctypes.data + idx * np.uint64(32 * inputs_g.shape[1])
-    g["vk"], g["vk_len"] = vg.ctypes.data, vg.size
-    p["kind"], p["n_inputs"], p["proof_len"] = KIND_PLONK, inputs_p.shape[1], proofs_p.shape[1]
-    p["proof"] = proofs_p.ctypes.data + idx * np.uint64(proofs_p.shape[1])
-    p["inputs"] = inputs_p.ctypes.data + idx * np.uint64(32 * inputs_p.shape[1])
-    p["vk"], p["vk_len"] = vp.ctypes.data, vp.size
-    rnd = None
-    if rnd_p is not None:
-        rnd = np.zeros((2 * n, 32), np.uint8)
-        rnd[1::2] = rnd_p
-    status = np.full(2 * n, STATUS_UNSET, dtype=np.uint8) if out is None else out
-    _check(lib.bn254v_verify_many(ctypes.cast(items.ctypes.data, POINTER(_Item)), 2 * n, sign_mode, _ptr(rnd),
-                                  _ptr(status)))
-    return status
+    """MixedItems(...).verify(...) in one step."""
+    return MixedItems(vk_g, proofs_g, inputs_g, vk_p, proofs_p, inputs_p, rnd_p).verify(sign_mode, out)
