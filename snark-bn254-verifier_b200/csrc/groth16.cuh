@@ -167,10 +167,9 @@ HD bool all_zero_bytes(const uint8_t* b, int n) {
   for (int i = 0; i < n; i++) t |= b[i];
   return t == 0;
 }
+// the points of one k-pair set; bit j of `skip`: pair j has an identity member (substituted by the generators)
 template <int KP>
-HD bool pairing_product_one(const uint8_t* g1, const uint8_t* g2, uint8_t* miller_out, uint8_t* gt_out) {
-  G1Aff p[KP];
-  G2Aff q[KP];
+HD uint32_t pairing_product_load(G1Aff* p, G2Aff* q, const uint8_t* g1, const uint8_t* g2) {
   uint32_t skip = 0;
   for (int j = 0; j < KP; j++) {
     if (all_zero_bytes(g1 + 64 * j, 64) || all_zero_bytes(g2 + 128 * j, 128)) {
@@ -182,6 +181,13 @@ HD bool pairing_product_one(const uint8_t* g1, const uint8_t* g2, uint8_t* mille
       load_g2_unchecked(q[j], g2 + 128 * j);
     }
   }
+  return skip;
+}
+template <int KP>
+HD bool pairing_product_one(const uint8_t* g1, const uint8_t* g2, uint8_t* miller_out, uint8_t* gt_out) {
+  G1Aff p[KP];
+  G2Aff q[KP];
+  const uint32_t skip = pairing_product_load<KP>(p, q, g1, g2);
   Fp12 f;
   miller_loop<KP, 0>(f, p, q, nullptr, nullptr, skip);
   if (miller_out) fp12_to_bytes(miller_out, f);

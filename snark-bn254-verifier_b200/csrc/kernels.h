@@ -86,8 +86,10 @@ struct PlonkArgs {
 int plonk_verify(cudaStream_t st, const PlonkArgs& a, int sm_count);
 
 // ---- raw pairing products
+// fbuf: m Fp12 of scratch (big batches run as two launches, Miller loops | final exponentiations) or null (one fused
+// launch); mid: an event recorded between the two launches, or null.  Returns the number of launches.
 int pairing_product(cudaStream_t st, int k, const uint8_t* g1, const uint8_t* g2, size_t m, uint8_t* is_one,
-                    uint8_t* miller_out, uint8_t* gt_out, int sm_count);
+                    uint8_t* miller_out, uint8_t* gt_out, int sm_count, Fp12* fbuf, cudaEvent_t mid);
 
 // ---- synthetic workloads and the roofline probe (k_aux.cu)
 int groth16_synth(cudaStream_t st, const Groth16Trapdoor& td, uint64_t seed, size_t first, size_t n, int n_public,
