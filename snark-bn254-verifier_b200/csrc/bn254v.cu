@@ -389,6 +389,9 @@ void vk_destroy(bn254v_vk* vk) {
   delete vk;
 }
 
+#ifndef BN_PLONK_CHUNK
+#define BN_PLONK_CHUNK ((size_t)1 << 18)  // PlonK proofs per pass of the staged kernels over one device's share
+#endif
 // ---- one device's share of a batch, on buffers already in device memory --------------------------------------
 struct StageEvents {  // optional CUDA events around the stages (device-resident timing runs)
   Dev* dev = nullptr;
@@ -397,8 +400,9 @@ struct StageEvents {  // optional CUDA events around the stages (device-resident
 int run_plonk_chunks(Dev& dev, const bn254v_vk* vk, int slot, const uint8_t* proofs, size_t stride, const uint32_t* lens,
                      const uint8_t* inputs, int n_inputs, const uint8_t* rnd, size_t m, uint8_t* status, uint8_t* g1,
                      uint8_t* fr, uint8_t* ml, uint8_t* gt, PlonkWork* work, int* list, int* count, bool timed) {
-  // chunks bound the per-proof workspace (PlonkWork, ~1.9 KB): 2^16 proofs -> 125 MB
-  const size_t CH = 1u << 16;
+  // chunks bound the per-proof workspace (PlonkWork, ~1.9 KB): 2^18 proofs -> 500 MB.  (2^16-proof chunks spent 5 % of
+  // their time in the short transcript / sum stages that cannot fill the GPU; they are amortised over a larger chunk.)
+  const size_t CH = BN_PLONK_CHUNK;
   const size_t in_bytes = (size_t)32 * n_inputs;
   for (size_t c0 = 0; c0 < m; c0 += CH) {
     const size_t cm = m - c0 < CH ? m - c0 : CH;
@@ -929,7 +933,7 @@ static int plonk_verify_batch_impl(const bn254v_vk* vk, const uint8_t* proofs, s
     if (p.fr.p) CU(cudaMemsetAsync(p.fr.p, 0, m * 256, dev.stream));
     if (p.m.p) CU(cudaMemsetAsync(p.m.p, 0, m * 384, dev.stream));
     if (p.gt.p) CU(cudaMemsetAsync(p.gt.p, 0, m * 384, dev.stream));
-    const size_t mc = m < (1u << 16) ? m : (1u << 16);
+    const size_t mc = m < BN_PLONK_CHUNK ? m : BN_PLONK_CHUNK;
     CU(p.work.alloc(mc * sizeof(PlonkWork)));
     CU(p.list.alloc(mc * sizeof(int)));
     CU(p.count.alloc(sizeof(int)));
@@ -1258,7 +1262,7 @@ int bn254v_plonk_batch_upload(const bn254v_vk* vk, const uint8_t* proofs, size_t
     size_t m = p.hi - p.lo;
     if (!m) continue;
     Dev& dev = g_devs[d];
-    const size_t mc = m < (1u << 16) ? m : (1u << 16);
+    const size_t mc = m < BN_PLONK_CHUNK ? m : BN_PLONK_CHUNK;
     BCU(cudaSetDevice(dev.id));
     BCU(cudaMalloc(&p.proofs, m * proof_stride));
     BCU(cudaMalloc(&p.inputs, m * in_bytes + 1));
@@ -1357,7 +1361,7 @@ static int batch_run(const bn254v_vk* vk, bn254v_batch* b, uint8_t* status, floa
         g_stage_n = 3;
       }
       // PlonK batches above 2^16 proofs run in chunks: the split is that of the first chunk, scaled to the whole time
-      if (b->kind == 1 && b->parts[0].hi - b->parts[0].lo > (1u << 16)) {
+      if (b->kind == 1 && b->parts[0].hi - b->parts[0].lo > BN_PLONK_CHUNK) {
         float sum = 0.f;
         for (int s = 0; s < n_stage; s++) sum += g_stage_ms[s];
         if (sum > 0.f)

@@ -47,10 +47,11 @@ __global__ void __launch_bounds__(64)
   }
 }
 
-#ifndef BN_TERMS_MINB
-#define BN_TERMS_MINB 8  // blocks of 64 threads per SM: <= 128 registers, 4 warps per sub-partition
-#endif
-__global__ void __launch_bounds__(64, BN_TERMS_MINB)
+// MINB blocks of 64 threads per SM: 8 = at most 128 registers, four warps per sub-partition (the per-term form and the
+// second MSM round); 1 = no register cap (255), which the joint form of the first round prefers (2^16 proofs: 5.93
+// against 6.28 ms; the second round 8.32 against 7.88 ms the other way round).
+template <int MINB>
+__global__ void __launch_bounds__(64, MINB)
     k_plonk_terms(const PlonkVkDev* __restrict__ vk, const uint8_t* __restrict__ proofs, size_t stride, PlonkWork* work,
                   const int* __restrict__ list, const int* __restrict__ count, int stage, int joint) {
   int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -175,11 +176,12 @@ int plonk_verify(cudaStream_t st, const PlonkArgs& a, int sm_count) {
   k_plonk_stage_a<<<g64, 64, 0, st>>>(a.vk, a.proofs, a.stride, a.lens, a.inputs, a.n_inputs, cm, a.status, a.work,
                                       a.list, a.count, dp);
   if (a.stage_ev) cudaEventRecord(a.stage_ev[0], st);
-  k_plonk_terms<<<dim3(g64, n0), 64, 0, st>>>(a.vk, a.proofs, a.stride, a.work, a.list, a.count, 0, joint);
+  if (joint) k_plonk_terms<1><<<dim3(g64, n0), 64, 0, st>>>(a.vk, a.proofs, a.stride, a.work, a.list, a.count, 0, joint);
+  else k_plonk_terms<8><<<dim3(g64, n0), 64, 0, st>>>(a.vk, a.proofs, a.stride, a.work, a.list, a.count, 0, joint);
   if (a.stage_ev) cudaEventRecord(a.stage_ev[1], st);
   k_plonk_stage_c<<<g64, 64, 0, st>>>(a.vk, a.proofs, a.stride, a.rnd, a.status, a.work, a.list, a.count, dp, joint);
   if (a.stage_ev) cudaEventRecord(a.stage_ev[2], st);
-  k_plonk_terms<<<dim3(g64, n1), 64, 0, st>>>(a.vk, a.proofs, a.stride, a.work, a.list, a.count, 1, joint);
+  k_plonk_terms<8><<<dim3(g64, n1), 64, 0, st>>>(a.vk, a.proofs, a.stride, a.work, a.list, a.count, 1, joint);
   if (a.stage_ev) cudaEventRecord(a.stage_ev[3], st);
   // Three lanes per proof while one proof per thread would leave the SM sub-partitions short of warps (the number
   // of survivors is only known on the device: the choice goes by the chunk size).

@@ -109,10 +109,10 @@ def test_full_size_batch_config3(gpu):
 
 
 def test_big_batch_several_chunks(gpu):
-    """150 000 proofs: three workspace chunks (2^16 proofs each at most), survivors listed per chunk; every status as
+    """600 000 proofs: three workspace chunks (2^18 proofs each at most), survivors listed per chunk; every status as
     expected."""
     import workloads
-    n = 150000
+    n = 600000
     proofs, inputs, rnd, expected = workloads.plonk_workload(n, seed=5)
     status = gpu.PlonkVerifier.verify_batch(proofs, plonk_vk_bytes(), inputs, rnd=rnd)
     assert (status == expected).all()
