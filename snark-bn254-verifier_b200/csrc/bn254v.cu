@@ -1072,7 +1072,9 @@ static int verify_many_impl(const bn254v_item* items, size_t n, int sign_mode, c
   // point), the host cores gather chunk k + 1 into the other pinned staging set: the gather of a large mixed batch (GBs)
   // is hidden behind the kernels.
   const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-  const size_t CH = (size_t)1 << 18;
+  // Chunk sizes: 2^20 Groth16 proofs (the multi-wave kernels gain efficiency up to there), 2^18 PlonK proofs (one
+  // workspace chunk); the very first chunk of the call is small so that the devices start early -- its gather is the
+  // only one that nothing hides.
   struct Task {
     Group* gr;
     size_t first, m;
@@ -1083,7 +1085,12 @@ static int verify_many_impl(const bn254v_item* items, size_t n, int sign_mode, c
       for (size_t j : gr.pos) status[j] = BN254V_PANIC_VK_PARSE;
       continue;
     }
-    for (size_t f = 0; f < gr.pos.size(); f += CH) tasks.push_back(Task{&gr, f, std::min(CH, gr.pos.size() - f)});
+    const size_t CH = (size_t)1 << (gr.kind == BN254V_KIND_GROTH16 ? 20 : 18);
+    for (size_t f = 0; f < gr.pos.size();) {
+      const size_t m = std::min(tasks.empty() ? (size_t)1 << 17 : CH, gr.pos.size() - f);
+      tasks.push_back(Task{&gr, f, m});
+      f += m;
+    }
   }
   struct Stage {
     PinnedBuf proofs, inputs, rnd, st, lens;

@@ -60,6 +60,23 @@ def test_mixed_batch_config5_parity(gpu):
     assert (status[1::2][idx] == st_c).all()
 
 
+def test_mixed_batch_of_several_chunks_per_group(gpu):
+    """600 000 items: both groups are cut into several chunks inside bn254v_verify_many (a small first chunk, then 2^20
+    Groth16 / 2^18 PlonK proofs), gathered into alternating staging sets while the previous chunk runs; every status
+    equals the generators' expectation and comes back at its item's position.  Verified twice over one prebuilt item
+    array (MixedItems), the second time into a caller-supplied buffer."""
+    import workloads
+    half = 300000
+    vk_g, pr_g, in_g, exp_g = gpu.groth16_synth(4242, half)
+    pr_p, in_p, rnd_p, exp_p = workloads.plonk_workload(half, seed=21)
+    items = gpu.MixedItems(vk_g, pr_g, in_g, plonk_vk_bytes(), pr_p, in_p, rnd_p)
+    status = items.verify()
+    assert (status[0::2] == exp_g).all() and (status[1::2] == exp_p).all()
+    out = np.full(2 * half, 255, np.uint8)
+    assert items.verify(out=out) is out
+    assert (out == status).all()
+
+
 def test_calls_from_several_host_threads(gpu):
     """The batch entry points share per-device streams and scratch pools: concurrent callers are serialised inside the
     library and every caller gets its own batch's answers."""
