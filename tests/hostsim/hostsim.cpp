@@ -456,6 +456,24 @@ void hs_groth16_vk_add_agg_tables(void* vkp) {
   }
   vk->agg_table = tab;  // (leaked with the VK: test process)
 }
+// [a + b lambda] P0 and P1 through the aggregate check's double-scalar routine (a, b: 8 bytes LE each); 0 on identity
+int hs_g1_mul_glv64_2(uint8_t* out128, const uint8_t* pts128, const uint8_t* a8, const uint8_t* b8) {
+  G1Aff p[2], r;
+  load_g1_unchecked(p[0], pts128);
+  load_g1_unchecked(p[1], pts128 + 64);
+  uint32_t a[2], b[2];
+  for (int k = 0; k < 2; k++) {
+    a[k] = (uint32_t)a8[4 * k] | ((uint32_t)a8[4 * k + 1] << 8) | ((uint32_t)a8[4 * k + 2] << 16) | ((uint32_t)a8[4 * k + 3] << 24);
+    b[k] = (uint32_t)b8[4 * k] | ((uint32_t)b8[4 * k + 1] << 8) | ((uint32_t)b8[4 * k + 2] << 16) | ((uint32_t)b8[4 * k + 3] << 24);
+  }
+  G1Jac res[2];
+  g1_mul_glv64_2(res, p, a, b);
+  for (int v = 0; v < 2; v++) {
+    if (!to_affine(r, res[v])) return 0;
+    store_g1(out128 + 64 * v, r);
+  }
+  return 1;
+}
 // multiply-adds of one proof's share of the aggregate check: [r] C, then validation + [r] A + the single-pair Miller loop
 unsigned long long hs_groth16_agg_proof_macs(void* vkp, const uint8_t* proof, uint32_t len, const uint8_t* inputs, int n_inputs,
                                              const uint8_t* rnd16, unsigned long long* prepare_part) {

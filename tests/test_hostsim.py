@@ -510,6 +510,25 @@ def test_plonk_joint_msm_form_gives_the_same_values(hs):
 
 
 # ------------------------------------------------------------------------------------------------ aggregate Groth16 check
+def test_signed_window_digit_patterns(hs):
+    """The signed 4-bit windows (digit = nibble of (k + 0x88..8) - 8) on scalars whose nibbles sit on the edges of the
+    digit range -- all 8 (every window carries into the next), all 7 (the largest digit without a carry), all 0xf,
+    alternating, a lone top bit -- through the aggregate check's double-scalar routine, whose 64-bit halves are windowed as they come:
+    [a + b lambda] P for two points sharing one table inversion, against the oracle."""
+    lam = 0xb3c4d79d41a917585bfc41088d8daaa78b17ea66b99c90dd
+    pats = [0x8888888888888888, 0x7777777777777777, 0xffffffffffffffff, 0x8000000000000000, 0x0000000000000001,
+            0x0f0f0f0f0f0f0f0f, 0xf0f0f0f0f0f0f0f1, 0x789abcdef0123457, 0x8888888877777777, 0x1]
+    p0, p1 = bo.g1_mul(bo.G1_GEN, 0x1234567), bo.g1_mul(bo.G1_GEN, bo.R - 77)
+    pts = bo.g1_to_bytes(p0) + bo.g1_to_bytes(p1)
+    out = ctypes.create_string_buffer(128)
+    for a in pats:
+        for b in pats + [0]:
+            k = (a + b * lam) % bo.R
+            assert hs.hs_g1_mul_glv64_2(out, pts, a.to_bytes(8, "little"), b.to_bytes(8, "little")) == 1
+            assert out.raw[:64] == bo.g1_to_bytes(bo.g1_mul(p0, k)), (hex(a), hex(b))
+            assert out.raw[64:] == bo.g1_to_bytes(bo.g1_mul(p1, k)), (hex(a), hex(b))
+
+
 def test_groth16_aggregate_check(hs):
     """csrc/groth16_agg.cuh on the host: the per-proof Miller values are ML(r_i A_i, B_i) of the oracle, an all-valid batch
     passes (with and without the window tables, for two fold widths), one invalid proof anywhere fails it, malformed
