@@ -182,7 +182,9 @@ HD int w4_digit(const uint32_t* v, int w) { return (int)((v[w >> 3] >> (4 * (w &
 // points by the VK loader), hence of order r: no multiple below r is the identity and no z is zero.  An affine entry
 // makes every window addition a mixed one (11 multiplications instead of 16) and takes 64 bytes instead of 96; the
 // affine coordinates of a multiple are unique, so the sums are the same group elements as with Jacobian entries.
-#define BN_MSM_MAX 3
+#ifndef BN_MSM_MAX
+#define BN_MSM_MAX 5
+#endif
 HD void g1_w4_tables(G1Aff* tab, const G1Aff* p, int n) {
   Fp z[7 * BN_MSM_MAX], c[7 * BN_MSM_MAX];
   Fp run = fe_one<FpCfg>();
