@@ -60,6 +60,21 @@ def test_full_size_config4_against_cpp_oracle(gpu):
     assert (ml == ml_c).all() and (gt == gt_c).all() and (one_c == expected[idx]).all()
 
 
+@pytest.mark.parametrize("n,k", [(60000, 2), (240000, 1)])
+def test_two_launch_shapes_write_the_same_values(gpu, n, k):
+    """Batches of more than one wave run as k_pairing_miller | k_pairing_finish (448 x 128 registers at 60 000 sets,
+    384 x 168 at 240 000): every is_one bit as constructed, and the canonical Miller / GT values those kernels write
+    are bit-exact against the C++ oracle on a strided sample."""
+    import os
+    import ref_cpu
+    g1, g2, expected = gpu.pairing_synth(77 + k, n, k=k)
+    is_one, ml, gt = gpu.pairing_product_batch(g1, g2, k, want_values=True)
+    assert (is_one == expected).all()
+    idx = np.arange(0, n, n // 96)
+    _, one_c, ml_c, gt_c = ref_cpu.pairing_product_batch(g1[idx], g2[idx], k, threads=os.cpu_count() or 1)
+    assert (ml[idx] == ml_c).all() and (gt[idx] == gt_c).all() and (one_c == expected[idx]).all()
+
+
 def test_identity_pairs_are_skipped(gpu):
     """A pair with an identity member (all-zero bytes) is skipped as in substrate-bn's pairing_batch: Miller and GT
     values are those of the remaining pairs (bit-exact against the oracle); a set of identities only gives 1."""
