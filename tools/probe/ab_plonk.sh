@@ -1,5 +1,5 @@
 # A/B of experiment builds on the PlonK path: every altlibs/*.so, then the in-tree library.  Usage: bash tools/probe/ab_plonk.sh
-for l in altlibs/*.so snark-bn254-verifier_b200/libbn254v.so; do
+for l in $(ls altlibs/*.so 2>/dev/null) snark-bn254-verifier_b200/libbn254v.so; do
   extra=$(sed 's/.*-fPIC//' $l.flags 2>/dev/null)
   echo "== $l [$extra]"
   for lg in 14 16 18; do
