@@ -570,6 +570,64 @@ HD Fe<C> fe_sqr(const Fe<C>& a) {
   return fe_mul(a, a);
 }
 
+// T[0..15] = a * a.  The 28 products a_i a_j, i < j, accumulate as in fe_mul_wide (position i + j even: E, odd: O; every
+// carry word is written before any product reaches it), their sum is doubled with funnel shifts and the 8 squares
+// a_i^2 go onto the aligned pairs (2i, 2i + 1) in one carry chain: 36 multiply-adds instead of 64.
+template <class C>
+HD void fe_sqr_wide(uint32_t* T, const Fe<C>& a) {
+  BN_COUNT_MACS(36);
+  uint32_t E[16], O[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) E[k] = O[k] = 0;
+#pragma unroll
+  for (int i = 0; i < 7; i++) {
+    const uint32_t ai = a.v[i];
+    // j = i + 2, i + 4, ..: position i + j even
+    if (i + 2 < 8) {
+#pragma unroll
+      for (int j = i + 2; j < 8; j += 2) {
+        E[i + j] = (j == i + 2) ? cc::mad_lo_cc(a.v[j], ai, E[i + j]) : cc::madc_lo_cc(a.v[j], ai, E[i + j]);
+        E[i + j + 1] = cc::madc_hi_cc(a.v[j], ai, E[i + j + 1]);
+      }
+      const int top = 2 * i + ((7 - i) & ~1);  // position of the last pair of the chain
+      if (top + 2 < 16) E[top + 2] = cc::addc(E[top + 2], 0u);
+    }
+    // j = i + 1, i + 3, ..: position i + j odd
+#pragma unroll
+    for (int j = i + 1; j < 8; j += 2) {
+      O[i + j] = (j == i + 1) ? cc::mad_lo_cc(a.v[j], ai, O[i + j]) : cc::madc_lo_cc(a.v[j], ai, O[i + j]);
+      O[i + j + 1] = cc::madc_hi_cc(a.v[j], ai, O[i + j + 1]);
+    }
+    {
+      const int top = 2 * i + 1 + ((6 - i) & ~1);
+      if (top + 2 < 16) O[top + 2] = cc::addc(O[top + 2], 0u);
+    }
+  }
+  uint32_t S[16];
+  S[0] = 0;
+  S[1] = cc::add_cc(E[1], O[1]);
+#pragma unroll
+  for (int k = 2; k < 15; k++) S[k] = cc::addc_cc(E[k], O[k]);
+  S[15] = cc::addc(E[15], O[15]);
+  // T = 2 S (S < 2^511), then + sum a_i^2 2^(64 i)
+  T[0] = 0;
+#pragma unroll
+  for (int k = 1; k < 16; k++) T[k] = (S[k] << 1) | (S[k - 1] >> 31);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    T[2 * i] = (i == 0) ? cc::mad_lo_cc(a.v[i], a.v[i], T[2 * i]) : cc::madc_lo_cc(a.v[i], a.v[i], T[2 * i]);
+    T[2 * i + 1] = (i == 7) ? cc::madc_hi(a.v[i], a.v[i], T[2 * i + 1]) : cc::madc_hi_cc(a.v[i], a.v[i], T[2 * i + 1]);
+  }
+}
+// a^2 / 2^256 mod m, fully reduced, for a < 2m (a^2 < m 2^256): 108 multiply-adds against the 136 of fe_mul(a, a).
+// Its own out-of-line copy: used by the G1 arithmetic (5 of the 7 multiplications of a doubling are squarings).
+template <class C>
+HDN Fe<C> fe_sqr_short(Fe<C> a) {
+  uint32_t T[16];
+  fe_sqr_wide(T, a);
+  return fe_redc_wide<C>(T);
+}
+
 template <class C>
 HD Fe<C> fe_to_mont(const Fe<C>& a) {
   Fe<C> r2;

@@ -203,7 +203,7 @@ HD void g1_w4_tables(G1Aff* tab, const G1Aff* p, int n) {
   for (int i = 7 * n - 1; i >= 0; i--) {
     const Fp zi = fe_mul(iv, c[i]);
     iv = fe_mul(iv, z[i]);
-    const Fp zi2 = fe_sqr(zi);
+    const Fp zi2 = fe_sqr_short(zi);
     G1Aff& e = tab[8 * (i / 7) + 1 + (i % 7)];
     e.x = fe_mul(e.x, zi2);
     e.y = fe_mul(e.y, fe_mul(zi2, zi));

@@ -14,7 +14,7 @@ HD Fp sub(const Fp& a, const Fp& b) { return fe_sub(a, b); }
 HD Fp neg(const Fp& a) { return fe_neg(a); }
 HD Fp dbl(const Fp& a) { return fe_dbl(a); }
 HD Fp mul(const Fp& a, const Fp& b) { return fe_mul(a, b); }
-HD Fp sqr(const Fp& a) { return fe_sqr(a); }
+HD Fp sqr(const Fp& a) { return fe_sqr_short(a); }  // (G1 arithmetic; the Fq2 code squares with fe_mul)
 HD bool is_zero(const Fp& a) { return fe_is_zero(a); }
 HD bool eq(const Fp& a, const Fp& b) { return fe_eq(a, b); }
 HD Fp inv(const Fp& a) { return fe_inv(a); }

@@ -18,6 +18,20 @@ void hs_fp_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   Fp z = fe_mul(x, y);
   memcpy(r, z.v, 32);
 }
+// the dedicated squaring of the G1 arithmetic (fe_sqr_short) in both fields; a may be any value below 2 m
+void hs_fe_sqr_short(int which, uint32_t* r, const uint32_t* a) {
+  if (which == 0) {
+    Fp x;
+    memcpy(x.v, a, 32);
+    Fp z = fe_sqr_short(x);
+    memcpy(r, z.v, 32);
+  } else {
+    Fr x;
+    memcpy(x.v, a, 32);
+    Fr z = fe_sqr_short(x);
+    memcpy(r, z.v, 32);
+  }
+}
 // 1 / a by divsteps (fe_inv) and by the Fermat chain (fe_inv_fermat); which: 0 = Fq, 1 = Fr.  Montgomery words in and out.
 void hs_fe_inv(int which, const uint32_t* a, uint32_t* inv_divsteps, uint32_t* inv_fermat) {
   if (which == 0) {

@@ -39,6 +39,25 @@ def test_montgomery_mul_both_fields(hs):
             assert _val(out) == a * b * rinv % mod
 
 
+def test_dedicated_squaring_both_fields(hs):
+    """fe_sqr_short (36 + 72 multiply-adds: off-diagonal products once, doubled, plus the squares) equals a * a / 2^256
+    mod m for random values, for every value below 2 m that the callers may pass (operand sums), and for limb patterns
+    that drive every carry of the accumulation (all-ones limbs, single limbs, alternating)."""
+    import random
+    rng = random.Random(7)
+    for which, mod in ((0, bo.P), (1, bo.R)):
+        rinv = pow(1 << 256, -1, mod)
+        vals = [rng.randrange(mod) for _ in range(300)] + [rng.randrange(mod, 2 * mod) for _ in range(100)]
+        vals += [0, 1, mod - 1, mod, mod + 1, 2 * mod - 1, (1 << 255) - 1, (1 << 254) - 1]
+        vals += [0xFFFFFFFF << (32 * i) for i in range(8) if (0xFFFFFFFF << (32 * i)) < 2 * mod]
+        vals += [v for v in (int("ffffffff00000000" * 4, 16) >> 2, int("00000000ffffffff" * 4, 16), int("f" * 63, 16) >> 1)
+                 if v < 2 * mod]
+        for a in (v for v in vals if v < 2 * mod):
+            out = (ctypes.c_uint32 * 8)()
+            hs.hs_fe_sqr_short(which, out, _limbs(a))
+            assert _val(out) == a * a * rinv % mod, hex(a)
+
+
 def test_divsteps_inversion_equals_fermat_and_python(hs):
     """fe_inv (Bernstein-Yang divsteps, 20 x 30) against the Fermat chain and against Python's pow, both fields: random
     values, small and near-modulus values, sparse limbs, powers of two, zero."""
