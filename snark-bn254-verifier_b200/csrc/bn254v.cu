@@ -33,6 +33,7 @@ struct Dev {
   cudaEvent_t ev[8];  // stage boundaries of the device-resident runs: ev[0] start ... ev[k] end of stage k
   cudaStream_t side;  // second stream and its two ordering events (aggregate Groth16 check)
   cudaEvent_t side_ev[2];
+  cudaEvent_t lane_ev[2];  // bn254v_verify_many: "the kernels of the chunk on lane 0 / 1 are done" (see Lane)
 };
 
 std::mutex g_mu;
@@ -171,15 +172,27 @@ struct PinnedBuf {
   T* as() { return (T*)p; }
 };
 
+// Lane: which of a device's two streams a batch call runs on.  The exported entry points use lane 0 alone.
+// bn254v_verify_many keeps two chunks in flight, one per lane: the copies of a chunk to the device run while the kernels
+// of the chunk before it are still going, and its kernels are ordered behind them by an event (kernels of two chunks
+// side by side would only slow each other down), so the device goes from the kernels of one chunk straight to those of
+// the next.  `chained`: wait for the other lane's kernels before launching, record this lane's event after them.
+struct Lane {
+  int id = 0;
+  bool chained = false;
+  cudaStream_t stream(const Dev& d) const { return id ? d.side : d.stream; }
+};
 // Declared AFTER the per-device buffers of a batch call, so that it is destroyed BEFORE them on every exit path --
 // including the early returns of CU() -- and no asynchronous copy still uses caller memory, or a scratch block that is
 // about to go back to the pool, when the function returns.
 struct SyncGuard {
+  int lane;  // -1: both streams
+  explicit SyncGuard(int lane_ = -1) : lane(lane_) {}
   ~SyncGuard() {
     for (auto& d : g_devs) {
       cudaSetDevice(d.id);
-      cudaStreamSynchronize(d.stream);
-      cudaStreamSynchronize(d.side);
+      if (lane != 1) cudaStreamSynchronize(d.stream);
+      if (lane != 0) cudaStreamSynchronize(d.side);
     }
   }
 };
@@ -397,7 +410,7 @@ struct StageEvents {  // optional CUDA events around the stages (device-resident
   Dev* dev = nullptr;
 };
 
-int run_plonk_chunks(Dev& dev, const bn254v_vk* vk, int slot, const uint8_t* proofs, size_t stride, const uint32_t* lens,
+int run_plonk_chunks(Dev& dev, cudaStream_t st, const bn254v_vk* vk, int slot, const uint8_t* proofs, size_t stride, const uint32_t* lens,
                      const uint8_t* inputs, int n_inputs, const uint8_t* rnd, size_t m, uint8_t* status, uint8_t* g1,
                      uint8_t* fr, uint8_t* ml, uint8_t* gt, PlonkWork* work, int* list, int* count, bool timed) {
   // chunks bound the per-proof workspace (PlonkWork, ~1.9 KB): 2^18 proofs -> 500 MB.  (2^16-proof chunks spent 5 % of
@@ -419,9 +432,9 @@ int run_plonk_chunks(Dev& dev, const bn254v_vk* vk, int slot, const uint8_t* pro
     a.dbg_m = ml ? ml + c0 * 384 : nullptr, a.dbg_gt = gt ? gt + c0 * 384 : nullptr;
     a.work = work, a.list = list, a.count = count;
     a.stage_ev = (timed && c0 == 0) ? &dev.ev[1] : nullptr;  // stage split of the first chunk
-    g_launches += launch::plonk_verify(dev.stream, a, g_sm_count);
+    g_launches += launch::plonk_verify(st, a, g_sm_count);
     CU(cudaGetLastError());
-    if (timed && c0 == 0) CU(cudaEventRecord(dev.ev[5], dev.stream));
+    if (timed && c0 == 0) CU(cudaEventRecord(dev.ev[5], st));
   }
   return 0;
 }
@@ -458,6 +471,7 @@ int bn254v_init(const int* devices, int n_devices) {
     for (auto& ev : d.ev) CU(cudaEventCreate(&ev));
     CU(cudaStreamCreateWithFlags(&d.side, cudaStreamNonBlocking));
     for (auto& ev : d.side_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : d.lane_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     g_devs.push_back(d);
   }
   g_inited = true;
@@ -476,6 +490,7 @@ void bn254v_shutdown(void) {
     cudaStreamSynchronize(d.side);
     cudaStreamDestroy(d.side);
     for (auto& ev : d.side_ev) cudaEventDestroy(ev);
+    for (auto& ev : d.lane_ev) cudaEventDestroy(ev);
   }
   PinnedBuf::release_all();
   g_devs.clear();
@@ -689,7 +704,7 @@ void bn254v_vk_cache_clear(void) {
 // bn254v_verify_many's helper thread calls while that call holds the lock.
 static int groth16_verify_batch_impl(const bn254v_vk* vk, const uint8_t* proofs, size_t proof_stride,
                                      const uint32_t* proof_len, const uint8_t* inputs_be, int n_inputs, size_t n,
-                                     uint8_t* status, const bn254v_debug* dbg) {
+                                     uint8_t* status, const bn254v_debug* dbg, Lane lane = Lane()) {
   if (!vk || vk->kind != BN254V_KIND_GROTH16 || !status || (n && (!proofs || (n_inputs > 0 && !inputs_be))) ||
       n_inputs < 0 || n_inputs > 64)
     return fail(BN254V_E_BAD_ARG, "bad argument");
@@ -702,7 +717,7 @@ static int groth16_verify_batch_impl(const bn254v_vk* vk, const uint8_t* proofs,
     DevBuf proofs, lens, inputs, status, l, m, gt, fbuf;
   };
   std::vector<Part> parts(nd);
-  SyncGuard guard;
+  SyncGuard guard(lane.id);
   const size_t in_bytes = (size_t)32 * n_inputs;
   for (int d = 0; d < nd; d++) {
     size_t lo, hi;
@@ -711,16 +726,17 @@ static int groth16_verify_batch_impl(const bn254v_vk* vk, const uint8_t* proofs,
     if (!m) continue;
     Part& p = parts[d];
     Dev& dev = g_devs[d];
+    const cudaStream_t st = lane.stream(dev);
     CU(cudaSetDevice(dev.id));
     CU(p.proofs.alloc(m * proof_stride));
     CU(p.inputs.alloc(m * in_bytes));
     CU(p.status.alloc(m));
-    CU(cudaMemcpyAsync(p.proofs.p, proofs + lo * proof_stride, m * proof_stride, cudaMemcpyHostToDevice, dev.stream));
+    CU(cudaMemcpyAsync(p.proofs.p, proofs + lo * proof_stride, m * proof_stride, cudaMemcpyHostToDevice, st));
     if (in_bytes)
-      CU(cudaMemcpyAsync(p.inputs.p, inputs_be + lo * in_bytes, m * in_bytes, cudaMemcpyHostToDevice, dev.stream));
+      CU(cudaMemcpyAsync(p.inputs.p, inputs_be + lo * in_bytes, m * in_bytes, cudaMemcpyHostToDevice, st));
     if (proof_len) {
       CU(p.lens.alloc(m * 4));
-      CU(cudaMemcpyAsync(p.lens.p, proof_len + lo, m * 4, cudaMemcpyHostToDevice, dev.stream));
+      CU(cudaMemcpyAsync(p.lens.p, proof_len + lo, m * 4, cudaMemcpyHostToDevice, st));
     }
     if (dbg && dbg->g1_out) CU(p.l.alloc(m * 64));
     if (dbg && dbg->miller_out) CU(p.m.alloc(m * 384));
@@ -730,16 +746,18 @@ static int groth16_verify_batch_impl(const bn254v_vk* vk, const uint8_t* proofs,
                           proof_len ? p.lens.as<uint32_t>() : nullptr, p.inputs.as<uint8_t>(), n_inputs, m,
                           p.status.as<uint8_t>(), p.l.as<uint8_t>(), p.m.as<uint8_t>(), p.gt.as<uint8_t>(),
                           p.fbuf.as<Fp12>(), nullptr};
-    g_launches += launch::groth16_verify(dev.stream, a, g_sm_count, nullptr);
+    if (lane.chained) CU(cudaStreamWaitEvent(st, dev.lane_ev[lane.id ^ 1], 0));
+    g_launches += launch::groth16_verify(st, a, g_sm_count, nullptr);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(status + lo, p.status.p, m, cudaMemcpyDeviceToHost, dev.stream));
-    if (p.l.p) CU(cudaMemcpyAsync(dbg->g1_out + lo * 64, p.l.p, m * 64, cudaMemcpyDeviceToHost, dev.stream));
-    if (p.m.p) CU(cudaMemcpyAsync(dbg->miller_out + lo * 384, p.m.p, m * 384, cudaMemcpyDeviceToHost, dev.stream));
-    if (p.gt.p) CU(cudaMemcpyAsync(dbg->gt_out + lo * 384, p.gt.p, m * 384, cudaMemcpyDeviceToHost, dev.stream));
+    if (lane.chained) CU(cudaEventRecord(dev.lane_ev[lane.id], st));
+    CU(cudaMemcpyAsync(status + lo, p.status.p, m, cudaMemcpyDeviceToHost, st));
+    if (p.l.p) CU(cudaMemcpyAsync(dbg->g1_out + lo * 64, p.l.p, m * 64, cudaMemcpyDeviceToHost, st));
+    if (p.m.p) CU(cudaMemcpyAsync(dbg->miller_out + lo * 384, p.m.p, m * 384, cudaMemcpyDeviceToHost, st));
+    if (p.gt.p) CU(cudaMemcpyAsync(dbg->gt_out + lo * 384, p.gt.p, m * 384, cudaMemcpyDeviceToHost, st));
   }
   for (int d = 0; d < nd; d++) {
     CU(cudaSetDevice(g_devs[d].id));
-    CU(cudaStreamSynchronize(g_devs[d].stream));
+    CU(cudaStreamSynchronize(lane.stream(g_devs[d])));
   }
   return BN254V_SUCCESS;
 }
@@ -884,7 +902,8 @@ static int groth16_batch_all_valid_impl(const bn254v_vk* vk, const uint8_t* proo
 
 static int plonk_verify_batch_impl(const bn254v_vk* vk, const uint8_t* proofs, size_t proof_stride,
                                    const uint32_t* proof_len, const uint8_t* inputs_be, int n_inputs,
-                                   const uint8_t* rnd_be, size_t n, uint8_t* status, const bn254v_debug* dbg) {
+                                   const uint8_t* rnd_be, size_t n, uint8_t* status, const bn254v_debug* dbg,
+                                   Lane lane = Lane()) {
   if (!vk || vk->kind != BN254V_KIND_PLONK || !status || (n && (!proofs || (n_inputs > 0 && !inputs_be))) ||
       n_inputs < 0 || n_inputs > BN_MAX_PLONK_PUBLIC)
     return fail(BN254V_E_BAD_ARG, "bad argument");
@@ -903,7 +922,7 @@ static int plonk_verify_batch_impl(const bn254v_vk* vk, const uint8_t* proofs, s
     DevBuf proofs, lens, inputs, rnd, status, g1, fr, m, gt, work, list, count;
   };
   std::vector<Part> parts(nd);
-  SyncGuard guard;
+  SyncGuard guard(lane.id);
   const size_t in_bytes = (size_t)32 * n_inputs;
   for (int d = 0; d < nd; d++) {
     size_t lo, hi;
@@ -912,45 +931,48 @@ static int plonk_verify_batch_impl(const bn254v_vk* vk, const uint8_t* proofs, s
     if (!m) continue;
     Part& p = parts[d];
     Dev& dev = g_devs[d];
+    const cudaStream_t st = lane.stream(dev);
     CU(cudaSetDevice(dev.id));
     CU(p.proofs.alloc(m * proof_stride));
     CU(p.inputs.alloc(m * in_bytes));
     CU(p.rnd.alloc(m * 32));
     CU(p.status.alloc(m));
-    CU(cudaMemcpyAsync(p.proofs.p, proofs + lo * proof_stride, m * proof_stride, cudaMemcpyHostToDevice, dev.stream));
+    CU(cudaMemcpyAsync(p.proofs.p, proofs + lo * proof_stride, m * proof_stride, cudaMemcpyHostToDevice, st));
     if (in_bytes)
-      CU(cudaMemcpyAsync(p.inputs.p, inputs_be + lo * in_bytes, m * in_bytes, cudaMemcpyHostToDevice, dev.stream));
-    CU(cudaMemcpyAsync(p.rnd.p, rnd_be + lo * 32, m * 32, cudaMemcpyHostToDevice, dev.stream));
+      CU(cudaMemcpyAsync(p.inputs.p, inputs_be + lo * in_bytes, m * in_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(p.rnd.p, rnd_be + lo * 32, m * 32, cudaMemcpyHostToDevice, st));
     if (proof_len) {
       CU(p.lens.alloc(m * 4));
-      CU(cudaMemcpyAsync(p.lens.p, proof_len + lo, m * 4, cudaMemcpyHostToDevice, dev.stream));
+      CU(cudaMemcpyAsync(p.lens.p, proof_len + lo, m * 4, cudaMemcpyHostToDevice, st));
     }
     if (dbg && dbg->g1_out) CU(p.g1.alloc(m * 256));
     if (dbg && dbg->fr_out) CU(p.fr.alloc(m * 256));
     if (dbg && dbg->miller_out) CU(p.m.alloc(m * 384));
     if (dbg && dbg->gt_out) CU(p.gt.alloc(m * 384));
-    if (p.g1.p) CU(cudaMemsetAsync(p.g1.p, 0, m * 256, dev.stream));
-    if (p.fr.p) CU(cudaMemsetAsync(p.fr.p, 0, m * 256, dev.stream));
-    if (p.m.p) CU(cudaMemsetAsync(p.m.p, 0, m * 384, dev.stream));
-    if (p.gt.p) CU(cudaMemsetAsync(p.gt.p, 0, m * 384, dev.stream));
+    if (p.g1.p) CU(cudaMemsetAsync(p.g1.p, 0, m * 256, st));
+    if (p.fr.p) CU(cudaMemsetAsync(p.fr.p, 0, m * 256, st));
+    if (p.m.p) CU(cudaMemsetAsync(p.m.p, 0, m * 384, st));
+    if (p.gt.p) CU(cudaMemsetAsync(p.gt.p, 0, m * 384, st));
     const size_t mc = m < BN_PLONK_CHUNK ? m : BN_PLONK_CHUNK;
     CU(p.work.alloc(mc * sizeof(PlonkWork)));
     CU(p.list.alloc(mc * sizeof(int)));
     CU(p.count.alloc(sizeof(int)));
-    rc = run_plonk_chunks(dev, vk, d, p.proofs.as<uint8_t>(), proof_stride, proof_len ? p.lens.as<uint32_t>() : nullptr,
+    if (lane.chained) CU(cudaStreamWaitEvent(st, dev.lane_ev[lane.id ^ 1], 0));
+    rc = run_plonk_chunks(dev, st, vk, d, p.proofs.as<uint8_t>(), proof_stride, proof_len ? p.lens.as<uint32_t>() : nullptr,
                           p.inputs.as<uint8_t>(), n_inputs, p.rnd.as<uint8_t>(), m, p.status.as<uint8_t>(),
                           p.g1.as<uint8_t>(), p.fr.as<uint8_t>(), p.m.as<uint8_t>(), p.gt.as<uint8_t>(),
                           p.work.as<PlonkWork>(), p.list.as<int>(), p.count.as<int>(), false);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(status + lo, p.status.p, m, cudaMemcpyDeviceToHost, dev.stream));
-    if (p.g1.p) CU(cudaMemcpyAsync(dbg->g1_out + lo * 256, p.g1.p, m * 256, cudaMemcpyDeviceToHost, dev.stream));
-    if (p.fr.p) CU(cudaMemcpyAsync(dbg->fr_out + lo * 256, p.fr.p, m * 256, cudaMemcpyDeviceToHost, dev.stream));
-    if (p.m.p) CU(cudaMemcpyAsync(dbg->miller_out + lo * 384, p.m.p, m * 384, cudaMemcpyDeviceToHost, dev.stream));
-    if (p.gt.p) CU(cudaMemcpyAsync(dbg->gt_out + lo * 384, p.gt.p, m * 384, cudaMemcpyDeviceToHost, dev.stream));
+    if (lane.chained) CU(cudaEventRecord(dev.lane_ev[lane.id], st));
+    CU(cudaMemcpyAsync(status + lo, p.status.p, m, cudaMemcpyDeviceToHost, st));
+    if (p.g1.p) CU(cudaMemcpyAsync(dbg->g1_out + lo * 256, p.g1.p, m * 256, cudaMemcpyDeviceToHost, st));
+    if (p.fr.p) CU(cudaMemcpyAsync(dbg->fr_out + lo * 256, p.fr.p, m * 256, cudaMemcpyDeviceToHost, st));
+    if (p.m.p) CU(cudaMemcpyAsync(dbg->miller_out + lo * 384, p.m.p, m * 384, cudaMemcpyDeviceToHost, st));
+    if (p.gt.p) CU(cudaMemcpyAsync(dbg->gt_out + lo * 384, p.gt.p, m * 384, cudaMemcpyDeviceToHost, st));
   }
   for (int d = 0; d < nd; d++) {
     CU(cudaSetDevice(g_devs[d].id));
-    CU(cudaStreamSynchronize(g_devs[d].stream));
+    CU(cudaStreamSynchronize(lane.stream(g_devs[d])));
   }
   return BN254V_SUCCESS;
 }
@@ -1132,17 +1154,18 @@ static int verify_many_impl(const bn254v_item* items, size_t n, int sign_mode, c
     }
     return 0;
   };
-  auto run = [&](Stage* sg) {
+  auto run = [&](Stage* sg, int lane_id) {
     Group& gr = *sg->t.gr;
+    const Lane lane{lane_id, true};
     if (gr.kind == BN254V_KIND_GROTH16)
       sg->rc = groth16_verify_batch_impl(gr.vk, sg->proofs.as<uint8_t>(), gr.stride,
                                            gr.ragged ? sg->lens.as<uint32_t>() : nullptr, sg->inputs.as<uint8_t>(),
-                                           gr.n_inputs, sg->t.m, sg->st.as<uint8_t>(), nullptr);
+                                           gr.n_inputs, sg->t.m, sg->st.as<uint8_t>(), nullptr, lane);
     else
       sg->rc = plonk_verify_batch_impl(gr.vk, sg->proofs.as<uint8_t>(), gr.stride,
                                          gr.ragged ? sg->lens.as<uint32_t>() : nullptr, sg->inputs.as<uint8_t>(),
                                          gr.n_inputs, sg->has_rnd ? sg->rnd.as<uint8_t>() : nullptr, sg->t.m,
-                                         sg->st.as<uint8_t>(), nullptr);
+                                         sg->st.as<uint8_t>(), nullptr, lane);
     if (sg->rc) sg->err = g_err;  // (thread-local in the helper thread)
   };
   auto collect = [&](Stage& sg) -> int {
@@ -1151,21 +1174,27 @@ static int verify_many_impl(const bn254v_item* items, size_t n, int sign_mode, c
     for (size_t j = 0; j < sg.t.m; j++) status[sg.t.gr->pos[sg.t.first + j]] = st[j];
     return 0;
   };
-  std::thread worker;
+  // Two chunks in flight, one per staging set and lane (see Lane): chunk k is gathered while chunk k - 1 runs and
+  // chunk k - 2 has been collected; its copies to the device go out as soon as it is gathered, its kernels queue up
+  // behind those of chunk k - 1.
+  std::thread workers[2];
   int result = 0;
   for (size_t k = 0; k < tasks.size() && !result; k++) {
     Stage& cur = stages[k & 1];
-    result = pack(cur, tasks[k]);
-    if (worker.joinable()) {
-      worker.join();
-      int r2 = collect(stages[(k - 1) & 1]);
-      if (!result) result = r2;
+    if (workers[k & 1].joinable()) {  // chunk k - 2: its staging set is the one to fill now
+      workers[k & 1].join();
+      result = collect(cur);
+      if (result) break;
     }
-    if (!result) worker = std::thread(run, &cur);
+    result = pack(cur, tasks[k]);
+    if (!result) workers[k & 1] = std::thread(run, &cur, (int)(k & 1));
   }
-  if (worker.joinable()) {
-    worker.join();
-    int r2 = collect(stages[(tasks.size() - 1) & 1]);
+  // the one or two chunks still running, older first
+  const size_t done = tasks.size();
+  for (size_t j = done >= 2 ? done - 2 : 0; j < done; j++) {
+    if (!workers[j & 1].joinable()) continue;
+    workers[j & 1].join();
+    const int r2 = collect(stages[j & 1]);
     if (!result) result = r2;
   }
   return result;
@@ -1337,7 +1366,7 @@ static int batch_run(const bn254v_vk* vk, bn254v_batch* b, uint8_t* status, floa
       CU(cudaEventRecord(dev.ev[2], dev.stream));
       if (d == 0) n_stage = 2;
     } else if (m && b->kind == 1) {
-      int rc = run_plonk_chunks(dev, vk, d, p.proofs, b->stride, nullptr, p.inputs, b->n_inputs, p.rnd, m, p.status,
+      int rc = run_plonk_chunks(dev, dev.stream, vk, d, p.proofs, b->stride, nullptr, p.inputs, b->n_inputs, p.rnd, m, p.status,
                                 nullptr, nullptr, nullptr, nullptr, p.work, p.list, p.count, true);
       if (rc) return rc;
       if (d == 0) n_stage = 5;
