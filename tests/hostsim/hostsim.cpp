@@ -32,6 +32,12 @@ void hs_fe_sqr_short(int which, uint32_t* r, const uint32_t* a) {
     memcpy(r, z.v, 32);
   }
 }
+// the plain 512-bit square under fe_sqr_short (any 256-bit a): 16 LE words
+void hs_fe_sqr_wide(uint32_t* t16, const uint32_t* a) {
+  Fp x;
+  memcpy(x.v, a, 32);
+  fe_sqr_wide(t16, x);
+}
 // 1 / a by divsteps (fe_inv) and by the Fermat chain (fe_inv_fermat); which: 0 = Fq, 1 = Fr.  Montgomery words in and out.
 void hs_fe_inv(int which, const uint32_t* a, uint32_t* inv_divsteps, uint32_t* inv_fermat) {
   if (which == 0) {

@@ -58,6 +58,20 @@ def test_dedicated_squaring_both_fields(hs):
             assert _val(out) == a * a * rinv % mod, hex(a)
 
 
+def test_wide_square_is_exact_for_every_limb_pattern(hs):
+    """fe_sqr_wide is a plain integer square: a * a over 16 words for ANY 256-bit a -- all-ones (every product and every
+    carry at its maximum), single limbs, alternating limbs, random values."""
+    import random
+    rng = random.Random(3)
+    vals = [(1 << 256) - 1, 0, 1, 1 << 255, (1 << 255) - 1, int("ffffffff00000000" * 4, 16), int("00000000ffffffff" * 4, 16)]
+    vals += [0xFFFFFFFF << (32 * i) for i in range(8)] + [((1 << 256) - 1) ^ (0xFFFFFFFF << (32 * i)) for i in range(8)]
+    vals += [rng.getrandbits(256) for _ in range(300)]
+    for a in vals:
+        out = (ctypes.c_uint32 * 16)()
+        hs.hs_fe_sqr_wide(out, _limbs(a))
+        assert sum(int(out[i]) << (32 * i) for i in range(16)) == a * a, hex(a)
+
+
 def test_divsteps_inversion_equals_fermat_and_python(hs):
     """fe_inv (Bernstein-Yang divsteps, 20 x 30) against the Fermat chain and against Python's pow, both fields: random
     values, small and near-modulus values, sparse limbs, powers of two, zero."""
